@@ -1,0 +1,855 @@
+// libdecaes_cuda: kernels + C ABI (include/decaes_cuda.h).  sm_100a only, no CPU fallback.
+//
+// Kernels
+//   basis_setup_kernel   EPG decay basis set and its flip-angle Jacobian for the whole angle grid,
+//                        once per call (thread_buffer_maker / EPGBasisSetEnsemble,
+//                        src/T2mapSEcorr.jl:339-407, 596-614; EPGJacobianFunctor src/EPGdecaycurve.jl:224-248)
+//   voxel_pipeline_kernel persistent one-warp CTAs; each warp pulls groups of 4 voxels and runs the
+//                        whole per-voxel chain (voxel.cuh) with its NNLS system in shared memory
+//   t2part_kernel        standalone T2part (src/T2partSEcorr.jl:95-138), one thread per voxel
+//   mock_image_kernel    synthetic MSE volume (src/utils.jl:623-658)
+//   dfma_peak_kernel     measured FP64 FMA peak for the roofline denominator
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/decaes_cuda.h"
+#include "voxel.cuh"
+
+using namespace decaes;
+
+// ============================================================================ device code
+
+// EPG value + d/dalpha (per degree) for one (angle, T2) pair; hand forward-mode through
+// epg_impulse_response! (src/EPGdecaycurve.jl:948-1028) and |sind(alpha/2) * .| (:936-946).
+#define EPG_MAXK 40  // supports ETL <= 72
+struct Dual {
+  double v, d;
+};
+__device__ static void epg_curve_jac(int ETL, double alpha_deg, double E1, double E2, double *dc, double *ddc,
+                                     int out_stride) {
+  const double kk = 0.017453292519943295;
+  double sina, cosa;
+  sincos(alpha_deg * kk, &sina, &cosa);
+  const double dsina = cosa * kk, dcosa = -sina * kk;
+  const double E2h = (E2 * E2) / 2, E1E2 = E1 * E2, E1sq = E1 * E1;
+  const double a = E2h, b = E2h * cosa, c = E1E2 * sina, d = E1sq * cosa, cp = -c / 2;
+  const double db = E2h * dcosa, dcc = E1E2 * dsina, dd = E1sq * dcosa, dcp = -dcc / 2;
+  const double m0 = sind_0_180(alpha_deg / 2);
+  double shalf, chalf;
+  {
+    double lo, hi = deg2rad_dd(alpha_deg / 2, lo);
+    sincos(hi, &shalf, &chalf);
+    chalf = fma(-shalf, lo, chalf);
+  }
+  const double dm0 = chalf * kk / 2;
+  Dual F[EPG_MAXK], Fb[EPG_MAXK], Z[EPG_MAXK];
+  auto emit = [&](int i, double v, double dv) {
+    double val = m0 * v, dval = dm0 * v + m0 * dv;
+    dc[i * out_stride] = fabs(val);
+    ddc[i * out_stride] = signbit(val) ? -dval : dval;
+  };
+  emit(0, a - b, -db);
+  F[1] = {a - b, -db}, Fb[1] = {0, 0}, Z[1] = {cp, dcp};
+  F[2] = {a + b, db}, Fb[2] = {0, 0}, Z[2] = {0, 0};
+  double C, S, Cp, Sp, dC, dS, dCp, dSp;
+  Dual vF, vFb, vZ;
+#define LOADK(k)                                                          \
+  C = F[k].v + Fb[k].v, S = F[k].v - Fb[k].v, dC = F[k].d + Fb[k].d, dS = F[k].d - Fb[k].d; \
+  Cp = a * C, Sp = b * S, dCp = a * dC, dSp = db * S + b * dS;            \
+  vFb.v = fma(-c, Z[k].v, Cp - Sp), vFb.d = (-dcc) * Z[k].v + (-c) * Z[k].d + (dCp - dSp); \
+  vF.v = fma(c, Z[k].v, Cp + Sp), vF.d = dcc * Z[k].v + c * Z[k].d + (dCp + dSp); \
+  vZ.v = fma(cp, S, d * Z[k].v), vZ.d = dcp * S + cp * dS + (dd * Z[k].v + d * Z[k].d)
+  for (int i = 2; i <= ETL - 1; i++) {
+    const bool first_half = (i <= ETL / 2);
+    const int kmax = first_half ? i : ETL - i + 1;
+    LOADK(1);
+    emit(i - 1, vFb.v, vFb.d);
+    F[1] = vFb, Z[1] = vZ;
+    Dual pend = vF;
+    for (int k = 2; k <= kmax; k++) {
+      LOADK(k);
+      F[k] = pend;
+      pend = vF;
+      Fb[k - 1] = vFb;
+      Z[k] = vZ;
+    }
+    F[kmax + 1] = pend;
+    if (first_half) Fb[i] = {0, 0}, Fb[i + 1] = {0, 0}, Z[i + 1] = {0, 0};
+  }
+  C = F[1].v + Fb[1].v, S = F[1].v - Fb[1].v, dC = F[1].d + Fb[1].d, dS = F[1].d - Fb[1].d;
+  double v = fma(-c, Z[1].v, fma(a, C, (-b) * S));
+  double dv = (-dcc) * Z[1].v + (-c) * Z[1].d + (a * dC - (db * S + b * dS));
+  emit(ETL - 1, v, dv);
+#undef LOADK
+}
+
+struct SetupParams {
+  int nTE, nT2, nA, ld, copy_elems;
+  double E1;
+  double angles[DECAES_MAX_ANGLES];
+  double E2[DECAES_MAX_NT2];
+  double *basis_rm, *basis_cm, *dbasis_cm;
+};
+
+__global__ void basis_setup_kernel(const __grid_constant__ SetupParams S) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S.nA * S.nT2) return;
+  int k = t / S.nT2, j = t % S.nT2;
+  double *dc = S.basis_cm + ((size_t)k * S.nT2 + j) * S.nTE;
+  double *ddc = S.dbasis_cm + ((size_t)k * S.nT2 + j) * S.nTE;
+  epg_curve_jac(S.nTE, S.angles[k], S.E1, S.E2[j], dc, ddc, 1);
+  double *rm = S.basis_rm + (size_t)k * S.copy_elems;
+  for (int i = 0; i < S.nTE; i++) rm[i * S.ld + j] = dc[i];
+  if (j == 0) {  // zero the padding so the bulk copy never moves uninitialised bytes
+    for (int i = 0; i < S.nTE; i++)
+      for (int jj = S.nT2; jj < S.ld; jj++) rm[i * S.ld + jj] = 0.0;
+    for (int e = S.nTE * S.ld; e < S.copy_elems; e++) rm[e] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(32) voxel_pipeline_kernel(const __grid_constant__ PipeParams P) {
+  extern __shared__ __align__(128) double smem[];
+  double *gscratch = P.scratch + (size_t)blockIdx.x * P.scratch_per_warp;
+  Warp W(P, smem, gscratch);
+  const int lane = lane_id();
+  if (lane == 0) {
+    mbar_init(W.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async();
+  __syncwarp();
+
+  const long long ngroups = (P.nvox + DECAES_GROUP - 1) / DECAES_GROUP;
+  unsigned long long processed = 0;
+  while (true) {
+    unsigned long long gidx = 0;
+    if (lane == 0) gidx = atomicAdd(&P.counters[0], 1ull);
+    gidx = __shfl_sync(DECAES_FULL_MASK, gidx, 0);
+    if ((long long)gidx >= ngroups) break;
+    const long long v0 = (long long)gidx * DECAES_GROUP;
+    // stage the group's signals: lane -> (echo offset, voxel) so that each load instruction touches
+    // 8 full 32-byte sectors (4 consecutive voxels per echo)
+    {
+      const int q = lane & 3, eo = lane >> 2;
+      for (int e = eo; e < P.nTE; e += 8) {
+        long long v = v0 + q;
+        W.sig[q * P.nTE + e] = (v < P.nvox) ? __ldg(P.image + v + (long long)e * P.stride) : 0.0;
+      }
+    }
+    __syncwarp();
+    for (int q = 0; q < DECAES_GROUP; q++) {
+      const long long v = v0 + q;
+      if (v >= P.nvox) break;
+      const double *signal = W.sig + q * P.nTE;
+      if (signal[0] > P.Threshold) {  // src/T2mapSEcorr.jl:177
+        W.process(v, signal);
+        processed++;
+      } else {
+        // skipped voxel: outputs are NaN (the reference pre-fills NaN, src/T2mapSEcorr.jl:36-52)
+        const double nanv = CUDART_NAN;
+        if (lane == 0) {
+          P.gdn[v] = nanv, P.ggm[v] = nanv, P.gva[v] = nanv, P.fnr[v] = nanv, P.snr[v] = nanv;
+          if (!P.alpha_provided) P.alpha[v] = nanv;
+          if (P.mu && P.chi2factor) P.mu[v] = nanv, P.chi2factor[v] = nanv;
+          if (P.resnorm) P.resnorm[v] = nanv;
+          if (P.has_part) P.sfr[v] = nanv, P.sgm[v] = nanv, P.mfr[v] = nanv, P.mgm[v] = nanv;
+        }
+        for (int j = lane; j < P.nT2; j += 32) P.dist[v + (long long)j * P.stride] = nanv;
+        if (P.decaycurve)
+          for (int i = lane; i < P.nTE; i += 32) P.decaycurve[v + (long long)i * P.stride] = nanv;
+        if (P.decaybasis && !P.fixed_alpha)
+          for (int k = lane; k < P.nTE * P.nT2; k += 32) P.decaybasis[v + (long long)k * P.stride] = nanv;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    if (processed) atomicAdd(&P.counters[1], processed);
+    if (W.n_early) atomicAdd(&P.counters[2], W.n_early);
+    if (W.n_overflow) atomicAdd(&P.counters[3], W.n_overflow);
+  }
+}
+
+struct PartParams {
+  int nT2, sp_lo, sp_hi, mp_lo, mp_hi, has_sigmoid;
+  long long nvox, stride;
+  const double *dist;
+  double *sfr, *sgm, *mfr, *mgm;
+  double logT2[DECAES_MAX_NT2], weights[DECAES_MAX_NT2];
+};
+
+// voxelwise_T2_parts!  src/T2partSEcorr.jl:95-138 — one thread per voxel, bins strided by `stride`
+// so that a warp reads 32 consecutive voxels of each bin (coalesced).
+__global__ void t2part_kernel(const __grid_constant__ PartParams Q) {
+  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= Q.nvox) return;
+  double S = 0, Ssp = 0, Smp = 0, dsp = 0, dmp = 0, dw = 0;
+  bool isn = false;
+  for (int j = 0; j < Q.nT2; j++) {
+    double dj = Q.dist[v + (long long)j * Q.stride];
+    isn |= isnan(dj);
+    S += dj;
+    if (j >= Q.sp_lo && j <= Q.sp_hi) dsp += dj * Q.logT2[j], Ssp += dj;
+    if (j >= Q.mp_lo && j <= Q.mp_hi) dmp += dj * Q.logT2[j], Smp += dj;
+    if (Q.has_sigmoid) dw = fma(dj, Q.weights[j], dw);
+  }
+  if (isn) return;
+  if (S > 0) {
+    Q.sfr[v] = Q.has_sigmoid ? dw / S : Ssp / S;
+    Q.mfr[v] = Smp / S;
+  }
+  if (Ssp > 0) Q.sgm[v] = exp(dsp / Ssp);
+  if (Smp > 0) Q.mgm[v] = exp(dmp / Smp);
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double urand(uint64_t seed, uint64_t vox, uint64_t k) {
+  uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ULL * (vox + 1));
+  h = mix64(h + 0x9E3779B97F4A7C15ULL * (k + 1));
+  return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// mock_image  src/utils.jl:623-658 with a per-voxel flip angle ~ U(120,180)
+__global__ void mock_image_kernel(double *image, long long nvox, long long stride, long long first_voxel, int nTE,
+                                  double TE, double T1, double sigma, uint64_t seed) {
+  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  uint64_t gid = (uint64_t)(first_voxel + v);
+  double sfr = 0.05 + (0.25 - 0.05) * urand(seed, gid, 0);
+  double T21 = 10e-3 + (20e-3 - 10e-3) * urand(seed, gid, 1);
+  double T22 = 50e-3 + (100e-3 - 50e-3) * urand(seed, gid, 2);
+  double alpha = 120.0 + 60.0 * urand(seed, gid, 3);
+  double E1 = exp(-(TE / 2) / T1);
+  double d1[72], d2[72], dd[72];
+  epg_curve_jac(nTE, alpha, E1, exp(-(TE / 2) / T21), d1, dd, 1);
+  epg_curve_jac(nTE, alpha, E1, exp(-(TE / 2) / T22), d2, dd, 1);
+  for (int k = 0; k < nTE; k++) {
+    double m = sfr * d1[k] + (1 - sfr) * d2[k];
+    double u1 = urand(seed, gid, 4 + 2 * (uint64_t)k), u2 = urand(seed, gid, 5 + 2 * (uint64_t)k);
+    double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    double zR = sigma * r * cs, zI = sigma * r * sn;
+    image[v + (long long)k * stride] = sqrt((m + zR) * (m + zR) + zI * zI);
+  }
+}
+
+// independent DFMA chains, 8 per thread
+__global__ void dfma_peak_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c), a1 = fma(a1, m, c), a2 = fma(a2, m, c), a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c), a5 = fma(a5, m, c), a6 = fma(a6, m, c), a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ============================================================================ host code
+
+static thread_local char g_err[512] = "";
+static thread_local decaes_run_stats g_stats;
+
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(DECAES_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- option checks: the assertions of T2mapOptions / T2partOptions (src/types.jl:28-84, 148-168) ----
+static int validate_map(const decaes_t2map_opts *o) {
+  if (!o) return fail(DECAES_EINVAL, "opts is NULL");
+  if (!(o->nx >= 1 && o->ny >= 1 && o->nz >= 1)) return fail(DECAES_EINVAL, "MatrixSize must be a tuple of 3 positive integers");
+  if (!(o->nTE >= 4)) return fail(DECAES_EINVAL, "At least four echoes are required for T2 mapping, but nTE = %d.", o->nTE);
+  if (!(o->TE > 0.0)) return fail(DECAES_EINVAL, "Echo spacing must be positive, but TE = %g.", o->TE);
+  if (!(o->nT2 >= 2)) return fail(DECAES_EINVAL, "At least two T2 components are required for T2 mapping, but nT2 = %d.", o->nT2);
+  if (!(0.0 < o->T2min && o->T2min < o->T2max)) return fail(DECAES_EINVAL, "T2Range must a sorted 2-tuple of positive values");
+  if (!(o->T1 > 0.0)) return fail(DECAES_EINVAL, "T1 must be positive, but T1 = %g.", o->T1);
+  if (!(o->Threshold >= 0.0 || o->Threshold == -INFINITY))
+    return fail(DECAES_EINVAL, "First echo signal threshold must be non-negative or -Inf");
+  if (!(0.0 <= o->MinRefAngle && o->MinRefAngle <= 180.0)) return fail(DECAES_EINVAL, "Minimum refocusing angle must be in the range [0, 180]");
+  if (!(o->nRefAngles >= 2)) return fail(DECAES_EINVAL, "nRefAngles must be at least 2, but nRefAngles = %d.", o->nRefAngles);
+  if (!(2 <= o->nRefAnglesMin && o->nRefAnglesMin <= o->nRefAngles))
+    return fail(DECAES_EINVAL, "nRefAnglesMin must be in the range [2, nRefAngles]");
+  if (!(o->reg >= DECAES_REG_NONE && o->reg <= DECAES_REG_MDP)) return fail(DECAES_EINVAL, "Unrecognized regularization method: %d", o->reg);
+  if (o->reg == DECAES_REG_CHI2 && !(o->Chi2Factor > 1.0)) return fail(DECAES_EINVAL, "Chi2Factor must be greater than 1.0");
+  if (o->reg == DECAES_REG_MDP && !(o->NoiseLevel > 0.0)) return fail(DECAES_EINVAL, "Noise level must be positive");
+  if (!(0.0 <= o->RefConAngle && o->RefConAngle <= 180.0)) return fail(DECAES_EINVAL, "Refocusing control angle must be in the range [0, 180]");
+  if (!std::isnan(o->SetFlipAngle) && !(0.0 <= o->SetFlipAngle && o->SetFlipAngle <= 180.0))
+    return fail(DECAES_EINVAL, "Fixed flip angle must be in the range [0, 180]");
+  if (o->legacy) return fail(DECAES_EUNSUPPORTED, "legacy = true is outside the accelerated path");
+  if (o->RefConAngle != 180.0) return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 is not accelerated yet");
+  if (o->nT2 > DECAES_MAX_NT2) return fail(DECAES_EUNSUPPORTED, "nT2 > %d is not supported", DECAES_MAX_NT2);
+  if (o->nRefAngles > DECAES_MAX_ANGLES) return fail(DECAES_EUNSUPPORTED, "nRefAngles > %d is not supported", DECAES_MAX_ANGLES);
+  if (o->nTE > 72) return fail(DECAES_EUNSUPPORTED, "nTE > 72 is not supported");
+  return DECAES_OK;
+}
+static int validate_part(const decaes_t2part_opts *o) {
+  if (!o) return fail(DECAES_EINVAL, "part opts is NULL");
+  if (!(o->nx >= 1 && o->ny >= 1 && o->nz >= 1)) return fail(DECAES_EINVAL, "MatrixSize must be positive");
+  if (!(o->nT2 >= 2)) return fail(DECAES_EINVAL, "nT2 must be at least 2");
+  if (!(0.0 < o->T2min && o->T2min < o->T2max)) return fail(DECAES_EINVAL, "T2Range must be sorted and positive");
+  if (!(o->SPWin_lo < o->SPWin_hi)) return fail(DECAES_EINVAL, "SPWin must be sorted");
+  if (!(o->MPWin_lo < o->MPWin_hi)) return fail(DECAES_EINVAL, "MPWin must be sorted");
+  if (!std::isnan(o->Sigmoid) && !(o->Sigmoid > 0)) return fail(DECAES_EINVAL, "Sigmoid must be positive");
+  if (o->nT2 > DECAES_MAX_NT2) return fail(DECAES_EUNSUPPORTED, "nT2 > %d is not supported", DECAES_MAX_NT2);
+  return DECAES_OK;
+}
+
+// ---- host tables ----
+// range(a, b; length = n) is evaluated in twice-precision by Julia; long double stands in.
+static void linrange(double a, double b, int n, double *out) {
+  if (n == 1) {
+    out[0] = a;
+    return;
+  }
+  for (int i = 0; i < n; i++)
+    out[i] = (double)(((long double)a * (long double)(n - 1 - i) + (long double)b * (long double)i) / (long double)(n - 1));
+  out[0] = a, out[n - 1] = b;
+}
+static void logrange(double a, double b, int n, double *out) {  // src/utils.jl:7
+  linrange(std::log(a), std::log(b), n, out);
+  for (int i = 0; i < n; i++) out[i] = std::exp(out[i]);
+  out[0] = a, out[n - 1] = b;
+}
+
+// probe order of initialize! (src/splines.jl:716-734): depends only on the grid size and budgets
+struct SeedState {
+  std::vector<char> seen;
+  std::vector<int> order;
+  int numeval = 0;
+};
+static void seed_eval_box(SeedState &s, int lo, int hi, int maxeval) {
+  int cs[2] = {lo, hi};
+  for (int k = 0; k < 2; k++) {
+    if (s.seen[lo] && s.seen[hi]) break;
+    if (s.numeval >= maxeval) break;
+    if (s.seen[cs[k]]) continue;
+    s.seen[cs[k]] = 1, s.order.push_back(cs[k]), s.numeval++;
+    if (s.numeval >= maxeval) break;
+  }
+}
+static void seed_rec(SeedState &s, int lo, int hi, int depth, int mineval, int maxeval) {
+  if (depth <= 0) return;
+  seed_eval_box(s, lo, hi, maxeval);
+  if (s.numeval >= mineval) return;
+  int mid = (lo + hi) / 2;  // 0-based midpoint of 1-based (lo+hi)/2: ((lo+1)+(hi+1))/2 - 1
+  mid = ((lo + 1) + (hi + 1)) / 2 - 1;
+  seed_rec(s, lo, mid, depth - 1, mineval, maxeval);
+  seed_rec(s, mid, hi, depth - 1, mineval, maxeval);
+}
+static std::vector<int> seed_order(int n, int mineval, int maxeval) {
+  SeedState s;
+  s.seen.assign(n, 0);
+  for (int depth = 1; depth <= mineval; depth++) {
+    seed_rec(s, 0, n - 1, depth, mineval, maxeval);
+    if (s.numeval >= mineval) break;
+  }
+  return s.order;
+}
+
+static double erfinv_newton(double y) {
+  double x = 0.0;
+  for (int it = 0; it < 100; it++) {
+    double dx = (std::erf(x) - y) / (1.1283791670955126 * std::exp(-x * x));
+    x -= dx;
+    if (std::fabs(dx) < 1e-16 * std::max(1.0, std::fabs(x))) break;
+  }
+  return x;
+}
+
+struct PartTables {
+  int sp_lo, sp_hi, mp_lo, mp_hi, has_sigmoid;  // 0-based inclusive
+  double logT2[DECAES_MAX_NT2], weights[DECAES_MAX_NT2];
+};
+// thread_buffer_maker(::T2partOptions)  src/T2partSEcorr.jl:143-164
+static int make_part_tables(const decaes_t2part_opts *o, PartTables *t) {
+  const int n = o->nT2;
+  double T2[DECAES_MAX_NT2];
+  logrange(o->T2min, o->T2max, n, T2);
+  for (int j = 0; j < n; j++) t->logT2[j] = std::log(T2[j]), t->weights[j] = 0.0;
+  int f;
+  for (f = 0; f < n && !(T2[f] >= o->SPWin_lo); f++) {}
+  int sp_lo = f < n ? f : -1;
+  for (f = n - 1; f >= 0 && !(T2[f] <= o->SPWin_hi); f--) {}
+  int sp_hi = f;
+  for (f = 0; f < n && !(T2[f] >= o->MPWin_lo); f++) {}
+  int mp_lo = f < n ? f : -1;
+  for (f = n - 1; f >= 0 && !(T2[f] <= o->MPWin_hi); f--) {}
+  int mp_hi = f;
+  if (sp_lo < 0 || sp_hi < 0 || mp_lo < 0 || mp_hi < 0)
+    return fail(DECAES_EINVAL, "SPWin/MPWin do not intersect the T2 grid (findfirst/findlast returned nothing)");
+  t->sp_lo = sp_lo, t->sp_hi = sp_hi, t->mp_lo = mp_lo, t->mp_hi = mp_hi;
+  t->has_sigmoid = !std::isnan(o->Sigmoid);
+  if (t->has_sigmoid) {  // sigmoid_weights  :155-164
+    double sigma = std::fabs(o->Sigmoid / (std::sqrt(2.0) * erfinv_newton(2 * 0.1 - 1)));
+    for (int j = 0; j < n; j++) {
+      double w = std::erfc(((T2[j] - o->SPWin_hi) / sigma) / std::sqrt(2.0)) / 2;
+      t->weights[j] = w <= 2.220446049250313e-16 ? 0.0 : w;
+    }
+  }
+  return DECAES_OK;
+}
+
+// ---- per-device workspace (grow-only, cached across calls) ----
+struct DeviceWs {
+  double *basis_rm = nullptr, *basis_cm = nullptr, *dbasis_cm = nullptr, *scratch = nullptr;
+  unsigned long long *counters = nullptr;
+  size_t basis_rm_cap = 0, basis_cm_cap = 0, scratch_cap = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_pending = false;
+  int sm_count = 0;
+};
+static std::mutex g_ws_mutex;
+static DeviceWs g_ws[64];
+
+static int ensure(double **p, size_t *cap, size_t need_doubles) {
+  if (*cap >= need_doubles) return DECAES_OK;
+  if (*p) CUDA_TRY(cudaFree(*p));
+  *p = nullptr, *cap = 0;
+  CUDA_TRY(cudaMalloc(p, need_doubles * sizeof(double)));
+  *cap = need_doubles;
+  return DECAES_OK;
+}
+
+struct Plan {
+  PipeParams P;
+  SetupParams S;
+  int smem_bytes, grid;
+};
+
+// Build kernel parameters (everything except volume pointers) and make sure the device workspace fits.
+static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part, int dev, Plan *plan) {
+  PipeParams &P = plan->P;
+  SetupParams &S = plan->S;
+  memset(&P, 0, sizeof P);
+  memset(&S, 0, sizeof S);
+  const int nTE = o->nTE, nT2 = o->nT2;
+  const bool fixed = !std::isnan(o->SetFlipAngle);
+  const int nA = fixed ? 1 : o->nRefAngles;
+  P.nTE = nTE, P.nT2 = nT2, P.nA = nA, P.reg = o->reg;
+  P.ld = nT2 | 1;
+  P.copy_elems = (nTE * P.ld + 1) & ~1;
+  P.rows_alloc = (o->reg == DECAES_REG_NONE) ? nTE : nTE + nT2;
+  P.epg_kmax = nTE / 2 + 3;
+  int epg_elems = 3 * P.epg_kmax * 32;
+  P.a_elems = std::max(std::max(P.rows_alloc * P.ld, P.copy_elems), epg_elems);
+  P.a_elems = (P.a_elems + 1) & ~1;
+  P.fixed_alpha = fixed, P.alpha_provided = o->alpha_provided;
+  P.maxeval = o->nRefAngles;
+  P.TE = o->TE, P.T1 = o->T1, P.Threshold = o->Threshold, P.Chi2Factor = o->Chi2Factor;
+  P.NoiseLevel = o->NoiseLevel, P.SetFlipAngle = o->SetFlipAngle;
+  P.E1 = std::exp(-(o->TE / 2) / o->T1);
+  double T2[DECAES_MAX_NT2];
+  logrange(o->T2min, o->T2max, nT2, T2);
+  for (int j = 0; j < nT2; j++) P.logT2[j] = std::log(T2[j]), P.E2[j] = std::exp(-(o->TE / 2) / T2[j]);
+  if (fixed)
+    P.angles[0] = o->SetFlipAngle;
+  else
+    linrange(o->MinRefAngle, 180.0, nA, P.angles);
+  if (!fixed && !o->alpha_provided) {
+    std::vector<int> seeds = seed_order(nA, o->nRefAnglesMin, o->nRefAngles);
+    P.nseed = (int)seeds.size();
+    for (int i = 0; i < P.nseed; i++) P.seeds[i] = (int8_t)seeds[i];
+  }
+  if (part) {
+    PartTables pt;
+    int rc = make_part_tables(part, &pt);
+    if (rc) return rc;
+    if (part->nT2 != nT2) return fail(DECAES_EINVAL, "T2part nT2 (%d) != T2map nT2 (%d)", part->nT2, nT2);
+    P.has_part = 1, P.sp_lo = pt.sp_lo, P.sp_hi = pt.sp_hi, P.mp_lo = pt.mp_lo, P.mp_hi = pt.mp_hi;
+    P.has_sigmoid = pt.has_sigmoid;
+    memcpy(P.weights, pt.weights, sizeof pt.weights);
+  }
+
+  SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems);
+  plan->smem_bytes = L.total_bytes;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if ((size_t)plan->smem_bytes > prop.sharedMemPerBlockOptin)
+    return fail(DECAES_EUNSUPPORTED, "problem needs %d bytes of shared memory per warp (> %zu)", plan->smem_bytes,
+                prop.sharedMemPerBlockOptin);
+  CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, voxel_pipeline_kernel, 32, plan->smem_bytes));
+  if (occ < 1) return fail(DECAES_ECUDA, "voxel_pipeline_kernel cannot be resident (occupancy 0)");
+  plan->grid = occ * prop.multiProcessorCount;
+
+  ScratchLayout sl(nTE, nT2, P.copy_elems, o->reg == DECAES_REG_GCV);
+  P.scratch_per_warp = sl.total;
+
+  std::lock_guard<std::mutex> lk(g_ws_mutex);
+  DeviceWs &ws = g_ws[dev];
+  ws.sm_count = prop.multiProcessorCount;
+  int rc;
+  if ((rc = ensure(&ws.basis_rm, &ws.basis_rm_cap, (size_t)nA * P.copy_elems))) return rc;
+  size_t cm = (size_t)nA * nTE * nT2;
+  if (ws.basis_cm_cap < cm) {
+    if (ws.basis_cm) cudaFree(ws.basis_cm), cudaFree(ws.dbasis_cm);
+    ws.basis_cm = ws.dbasis_cm = nullptr, ws.basis_cm_cap = 0;
+    CUDA_TRY(cudaMalloc(&ws.basis_cm, cm * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&ws.dbasis_cm, cm * sizeof(double)));
+    ws.basis_cm_cap = cm;
+  }
+  if ((rc = ensure(&ws.scratch, &ws.scratch_cap, (size_t)plan->grid * sl.total))) return rc;
+  if (!ws.counters) CUDA_TRY(cudaMalloc(&ws.counters, 8 * sizeof(unsigned long long)));
+  for (int i = 0; i < 4; i++)
+    if (!ws.ev[i]) CUDA_TRY(cudaEventCreate(&ws.ev[i]));
+  P.basis_rm = ws.basis_rm, P.basis_cm = ws.basis_cm, P.dbasis_cm = ws.dbasis_cm;
+  P.scratch = ws.scratch, P.counters = ws.counters;
+
+  S.nTE = nTE, S.nT2 = nT2, S.nA = nA, S.ld = P.ld, S.copy_elems = P.copy_elems, S.E1 = P.E1;
+  memcpy(S.angles, P.angles, sizeof S.angles);
+  memcpy(S.E2, P.E2, sizeof S.E2);
+  S.basis_rm = ws.basis_rm, S.basis_cm = ws.basis_cm, S.dbasis_cm = ws.dbasis_cm;
+  return DECAES_OK;
+}
+
+static int check_out(const decaes_t2map_out *out, const decaes_t2part_opts *part) {
+  if (!out) return fail(DECAES_EINVAL, "out is NULL");
+  if (!out->gdn || !out->ggm || !out->gva || !out->fnr || !out->snr || !out->alpha || !out->dist)
+    return fail(DECAES_EINVAL, "gdn, ggm, gva, fnr, snr, alpha and dist outputs are required");
+  if (part && !(out->sfr && out->sgm && out->mfr && out->mgm))
+    return fail(DECAES_EINVAL, "fused T2part needs sfr, sgm, mfr and mgm outputs");
+  return DECAES_OK;
+}
+
+// enqueue setup + pipeline kernels on `stream` for device-resident data
+static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t nvox, int64_t stride,
+                           const decaes_t2map_out *o, cudaStream_t stream) {
+  PipeParams &P = plan.P;
+  P.image = d_image, P.nvox = nvox, P.stride = stride;
+  P.gdn = o->gdn, P.ggm = o->ggm, P.gva = o->gva, P.fnr = o->fnr, P.snr = o->snr, P.alpha = o->alpha, P.dist = o->dist;
+  P.resnorm = o->resnorm, P.decaycurve = o->decaycurve, P.mu = o->mu, P.chi2factor = o->chi2factor;
+  P.decaybasis = o->decaybasis;
+  P.sfr = o->sfr, P.sgm = o->sgm, P.mfr = o->mfr, P.mgm = o->mgm;
+  DeviceWs &ws = g_ws[dev];
+  CUDA_TRY(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream));
+  CUDA_TRY(cudaEventRecord(ws.ev[0], stream));
+  int nt = plan.S.nA * plan.S.nT2;
+  basis_setup_kernel<<<(nt + 63) / 64, 64, 0, stream>>>(plan.S);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(ws.ev[1], stream));
+  int64_t ngroups = (nvox + DECAES_GROUP - 1) / DECAES_GROUP;
+  int grid = (int)std::min<int64_t>(plan.grid, std::max<int64_t>(ngroups, 1));
+  voxel_pipeline_kernel<<<grid, 32, plan.smem_bytes, stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(ws.ev[2], stream));
+  ws.ev_pending = true;
+  return DECAES_OK;
+}
+
+static int collect_device_stats(int dev, decaes_run_stats *st) {
+  DeviceWs &ws = g_ws[dev];
+  if (!ws.ev_pending) return DECAES_OK;
+  CUDA_TRY(cudaEventSynchronize(ws.ev[2]));
+  float a = 0, b = 0;
+  CUDA_TRY(cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]));
+  CUDA_TRY(cudaEventElapsedTime(&b, ws.ev[1], ws.ev[2]));
+  unsigned long long c[8];
+  CUDA_TRY(cudaMemcpy(c, ws.counters, sizeof c, cudaMemcpyDeviceToHost));
+  st->setup_ms = std::max(st->setup_ms, (double)a);
+  st->pipeline_ms = std::max(st->pipeline_ms, (double)b);
+  st->voxels_processed += (int64_t)c[1];
+  st->kernel_launches += 2;
+  ws.ev_pending = false;
+  return DECAES_OK;
+}
+
+extern "C" {
+
+const char *decaes_last_error(void) { return g_err; }
+int decaes_abi_version(void) { return DECAES_ABI_VERSION; }
+
+int decaes_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void decaes_get_stats(decaes_run_stats *stats) {
+  // device-API calls leave their events pending; resolve them now
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && g_ws[dev].ev_pending) {
+    g_stats.ngpus_used = 1;
+    collect_device_stats(dev, &g_stats);
+  }
+  if (stats) *stats = g_stats;
+}
+
+int decaes_t2map_device(const double *d_image, int64_t nvox, int64_t stride, const decaes_t2map_opts *opts,
+                        const decaes_t2part_opts *part, const decaes_t2map_out *d_out, void *stream) {
+  int rc = validate_map(opts);
+  if (rc) return rc;
+  if (part && (rc = validate_part(part))) return rc;
+  if ((rc = check_out(d_out, part))) return rc;
+  if (!d_image || nvox < 0 || stride < nvox) return fail(DECAES_EINVAL, "bad image pointer / nvox / stride");
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  Plan plan;
+  if ((rc = make_plan(opts, part, dev, &plan))) return rc;
+  memset(&g_stats, 0, sizeof g_stats);
+  g_stats.voxels_total = nvox;
+  if (nvox == 0) return DECAES_OK;
+  return launch_pipeline(plan, dev, d_image, nvox, stride, d_out, (cudaStream_t)stream);
+}
+
+static int launch_part(const decaes_t2part_opts *part, const double *d_dist, int64_t nvox, int64_t stride, double *sfr,
+                       double *sgm, double *mfr, double *mgm, cudaStream_t stream) {
+  PartTables pt;
+  int rc = make_part_tables(part, &pt);
+  if (rc) return rc;
+  PartParams Q;
+  memset(&Q, 0, sizeof Q);
+  Q.nT2 = part->nT2, Q.sp_lo = pt.sp_lo, Q.sp_hi = pt.sp_hi, Q.mp_lo = pt.mp_lo, Q.mp_hi = pt.mp_hi;
+  Q.has_sigmoid = pt.has_sigmoid, Q.nvox = nvox, Q.stride = stride, Q.dist = d_dist;
+  Q.sfr = sfr, Q.sgm = sgm, Q.mfr = mfr, Q.mgm = mgm;
+  memcpy(Q.logT2, pt.logT2, sizeof pt.logT2);
+  memcpy(Q.weights, pt.weights, sizeof pt.weights);
+  if (nvox > 0) {
+    t2part_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, stream>>>(Q);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return DECAES_OK;
+}
+
+int decaes_t2part_device(const double *d_dist, int64_t nvox, int64_t stride, const decaes_t2part_opts *part,
+                         double *d_sfr, double *d_sgm, double *d_mfr, double *d_mgm, void *stream) {
+  int rc = validate_part(part);
+  if (rc) return rc;
+  if (!d_dist || !d_sfr || !d_sgm || !d_mfr || !d_mgm || nvox < 0 || stride < nvox)
+    return fail(DECAES_EINVAL, "bad pointers / nvox / stride");
+  return launch_part(part, d_dist, nvox, stride, d_sfr, d_sgm, d_mfr, d_mgm, (cudaStream_t)stream);
+}
+
+int decaes_mock_image_device(double *d_image, int64_t nvox, int64_t stride, int64_t first_voxel, int32_t nTE,
+                             double TE, double T1, double SNR, uint64_t seed, void *stream) {
+  if (!d_image || nvox < 0 || stride < nvox || nTE < 4 || nTE > 72) return fail(DECAES_EINVAL, "bad arguments");
+  if (nvox == 0) return DECAES_OK;
+  double sigma = std::pow(10.0, -SNR / 20);
+  mock_image_kernel<<<(unsigned)((nvox + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_image, nvox, stride, first_voxel,
+                                                                                     nTE, TE, T1, sigma, seed);
+  CUDA_TRY(cudaGetLastError());
+  return DECAES_OK;
+}
+
+int decaes_measure_fp64_peak(double *flops_per_s) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+  double *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double) * threads * blocks));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CUDA_TRY(cudaEventRecord(e0));
+    dfma_peak_kernel<<<blocks, threads>>>(d, iters);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, fl);
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(d);
+  if (flops_per_s) *flops_per_s = best;
+  return DECAES_OK;
+}
+
+int decaes_setup_tables(const decaes_t2map_opts *o, double *echotimes, double *t2times, double *refangleset,
+                        double *decaybasisset) {
+  int rc = validate_map(o);
+  if (rc) return rc;
+  const int nTE = o->nTE, nT2 = o->nT2;
+  const bool fixed = !std::isnan(o->SetFlipAngle);
+  const int nA = fixed ? 1 : o->nRefAngles;
+  if (echotimes)
+    for (int i = 0; i < nTE; i++) echotimes[i] = o->TE * (double)(i + 1);  // src/T2mapSEcorr.jl:28
+  if (t2times) logrange(o->T2min, o->T2max, nT2, t2times);
+  if (refangleset) {
+    if (fixed) refangleset[0] = o->SetFlipAngle; else linrange(o->MinRefAngle, 180.0, nA, refangleset);
+  }
+  if (decaybasisset) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    Plan plan;
+    if ((rc = make_plan(o, nullptr, dev, &plan))) return rc;
+    basis_setup_kernel<<<(nA * nT2 + 63) / 64, 64>>>(plan.S);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(decaybasisset, plan.S.basis_cm, sizeof(double) * (size_t)nA * nTE * nT2, cudaMemcpyDeviceToHost));
+  }
+  return DECAES_OK;
+}
+
+// ---------------------------------------------------------------------------- host-pointer API
+struct SlabJob {
+  int dev;
+  int64_t v0, v1;
+  int rc;
+  char err[512];
+  decaes_run_stats st;
+};
+
+static int run_slab(SlabJob &job, const double *image, int64_t Nvox, const decaes_t2map_opts *opts,
+                    const decaes_t2part_opts *part, const decaes_t2map_out *out) {
+  CUDA_TRY(cudaSetDevice(job.dev));
+  const int nTE = opts->nTE, nT2 = opts->nT2;
+  const int64_t nv = job.v1 - job.v0;
+  memset(&job.st, 0, sizeof job.st);
+  if (nv <= 0) return DECAES_OK;
+  Plan plan;
+  int rc = make_plan(opts, part, job.dev, &plan);
+  if (rc) return rc;
+  cudaStream_t st;
+  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  // one allocation for the slab: image + every requested output, all with stride nv
+  struct Field {
+    double *const *host;
+    int64_t mult;
+    size_t off;
+  };
+  double *hostp[16] = {out->gdn, out->ggm, out->gva, out->fnr, out->snr, out->alpha, out->dist, out->resnorm,
+                       out->decaycurve, out->mu, out->chi2factor, out->decaybasis, out->sfr, out->sgm, out->mfr, out->mgm};
+  int64_t mult[16] = {1, 1, 1, 1, 1, 1, nT2, 1, nTE, 1, 1, (int64_t)nTE * nT2, 1, 1, 1, 1};
+  if (!std::isnan(opts->SetFlipAngle)) hostp[11] = nullptr;  // shared basis is not a per-voxel output (:581-587)
+  if (!part) hostp[12] = hostp[13] = hostp[14] = hostp[15] = nullptr;
+  size_t total = (size_t)nv * nTE, off[16];
+  for (int f = 0; f < 16; f++) {
+    off[f] = total;
+    if (hostp[f]) total += (size_t)nv * mult[f];
+  }
+  double *dbuf = nullptr;
+  CUDA_TRY(cudaMalloc(&dbuf, total * sizeof(double)));
+  cudaEvent_t e0, e1, e2, e3;
+  cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventCreate(&e2), cudaEventCreate(&e3);
+  CUDA_TRY(cudaEventRecord(e0, st));
+  CUDA_TRY(cudaMemcpy2DAsync(dbuf, nv * sizeof(double), image + job.v0, Nvox * sizeof(double), nv * sizeof(double), nTE,
+                             cudaMemcpyHostToDevice, st));
+  decaes_t2map_out dout;
+  double **dptr = (double **)&dout;
+  for (int f = 0; f < 16; f++) dptr[f] = hostp[f] ? dbuf + off[f] : nullptr;
+  if (opts->alpha_provided)
+    CUDA_TRY(cudaMemcpyAsync(dout.alpha, out->alpha + job.v0, nv * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(e1, st));
+  rc = launch_pipeline(plan, job.dev, dbuf, nv, nv, &dout, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(e2, st));
+  for (int f = 0; f < 16; f++)
+    if (hostp[f])
+      CUDA_TRY(cudaMemcpy2DAsync(hostp[f] + job.v0, Nvox * sizeof(double), dptr[f], nv * sizeof(double), nv * sizeof(double),
+                                 mult[f], cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(e3, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  float h2d = 0, d2h = 0;
+  cudaEventElapsedTime(&h2d, e0, e1), cudaEventElapsedTime(&d2h, e2, e3);
+  job.st.h2d_ms = h2d, job.st.d2h_ms = d2h;
+  rc = collect_device_stats(job.dev, &job.st);
+  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2), cudaEventDestroy(e3);
+  cudaFree(dbuf);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+static std::mutex g_call_mutex;  // re-entrant host calls are serialised
+
+int decaes_t2map(const double *image, const decaes_t2map_opts *opts, const decaes_t2part_opts *part,
+                 const decaes_t2map_out *out) {
+  std::lock_guard<std::mutex> lk(g_call_mutex);
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = validate_map(opts);
+  if (rc) return rc;
+  if (part && (rc = validate_part(part))) return rc;
+  if ((rc = check_out(out, part))) return rc;
+  if (!image) return fail(DECAES_EINVAL, "image is NULL");
+  int ndev = decaes_device_count();
+  if (ndev < 1) return fail(DECAES_ECUDA, "no CUDA device available (libdecaes_cuda has no CPU fallback)");
+  int ng = opts->ngpus > 0 ? std::min(opts->ngpus, ndev) : ndev;
+  const int64_t Nvox = (int64_t)opts->nx * opts->ny * opts->nz;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  std::vector<SlabJob> jobs(ng);
+  // contiguous voxel slabs, boundaries aligned to the 4-voxel work group
+  for (int d = 0; d < ng; d++) {
+    int64_t a = (Nvox * d / ng) & ~(int64_t)(DECAES_GROUP - 1), b = (d == ng - 1) ? Nvox : ((Nvox * (d + 1) / ng) & ~(int64_t)(DECAES_GROUP - 1));
+    jobs[d].dev = (ng == 1) ? cur : d, jobs[d].v0 = a, jobs[d].v1 = b, jobs[d].rc = 0, jobs[d].err[0] = 0;
+  }
+  auto worker = [&](SlabJob &j) {
+    j.rc = run_slab(j, image, Nvox, opts, part, out);
+    if (j.rc) snprintf(j.err, sizeof j.err, "%s", g_err);
+  };
+  if (ng == 1) {
+    worker(jobs[0]);
+  } else {
+    std::vector<std::thread> th;
+    for (int d = 0; d < ng; d++) th.emplace_back(worker, std::ref(jobs[d]));
+    for (auto &t : th) t.join();
+  }
+  cudaSetDevice(cur);
+  memset(&g_stats, 0, sizeof g_stats);
+  g_stats.voxels_total = Nvox, g_stats.ngpus_used = ng;
+  for (auto &j : jobs) {
+    if (j.rc) return fail(j.rc, "device %d: %s", j.dev, j.err);
+    g_stats.voxels_processed += j.st.voxels_processed;
+    g_stats.kernel_launches += j.st.kernel_launches;
+    g_stats.setup_ms = std::max(g_stats.setup_ms, j.st.setup_ms);
+    g_stats.pipeline_ms = std::max(g_stats.pipeline_ms, j.st.pipeline_ms);
+    g_stats.h2d_ms = std::max(g_stats.h2d_ms, j.st.h2d_ms);
+    g_stats.d2h_ms = std::max(g_stats.d2h_ms, j.st.d2h_ms);
+  }
+  g_stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return DECAES_OK;
+}
+
+int decaes_t2part(const double *dist, const decaes_t2part_opts *part, double *sfr, double *sgm, double *mfr,
+                  double *mgm) {
+  std::lock_guard<std::mutex> lk(g_call_mutex);
+  int rc = validate_part(part);
+  if (rc) return rc;
+  if (!dist || !sfr || !sgm || !mfr || !mgm) return fail(DECAES_EINVAL, "NULL pointer");
+  if (decaes_device_count() < 1) return fail(DECAES_ECUDA, "no CUDA device available (libdecaes_cuda has no CPU fallback)");
+  const int64_t Nvox = (int64_t)part->nx * part->ny * part->nz;
+  const int nT2 = part->nT2;
+  double *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double) * (size_t)Nvox * (nT2 + 4)));
+  double *o[4] = {d + (size_t)Nvox * nT2, d + (size_t)Nvox * (nT2 + 1), d + (size_t)Nvox * (nT2 + 2), d + (size_t)Nvox * (nT2 + 3)};
+  double *h[4] = {sfr, sgm, mfr, mgm};
+  CUDA_TRY(cudaMemcpy(d, dist, sizeof(double) * (size_t)Nvox * nT2, cudaMemcpyHostToDevice));
+  // outputs keep the caller's pre-fill (NaN) wherever the reference would not write
+  for (int k = 0; k < 4; k++) CUDA_TRY(cudaMemcpy(o[k], h[k], sizeof(double) * Nvox, cudaMemcpyHostToDevice));
+  rc = launch_part(part, d, Nvox, Nvox, o[0], o[1], o[2], o[3], 0);
+  if (rc) {
+    cudaFree(d);
+    return rc;
+  }
+  for (int k = 0; k < 4; k++) CUDA_TRY(cudaMemcpy(h[k], o[k], sizeof(double) * Nvox, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaFree(d));
+  memset(&g_stats, 0, sizeof g_stats);
+  g_stats.voxels_total = Nvox, g_stats.ngpus_used = 1, g_stats.kernel_launches = 1;
+  return DECAES_OK;
+}
+
+}  // extern "C"

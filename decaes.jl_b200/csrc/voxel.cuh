@@ -1,0 +1,934 @@
+// Per-voxel pipeline executed by one warp: normalise -> flip-angle fit -> EPG basis at the fitted
+// angle -> regularised NNLS (none / lcurve / gcv / chi2 / mdp) -> output maps + T2part epilogue.
+//
+// Reference: voxelwise_T2_distribution! src/T2mapSEcorr.jl:201-238, optimize_flip_angle! :409-423,
+// T2_distribution! :475-505, save_results! :512-591, voxelwise_T2_parts! src/T2partSEcorr.jl:95-138,
+// surrogate search src/splines.jl:504-566, 705-850, 975-1041, choosers src/lsqnonneg.jl,
+// 1-D optimisers src/optimization.jl:71-128, 191-219, 319-413.
+#pragma once
+#include "nnls.cuh"
+
+namespace decaes {
+
+struct PipeParams {
+  // sizes
+  int nTE, nT2, ld, nA, reg;
+  int rows_alloc;       // rows of the shared working matrix (nTE or nTE + nT2)
+  int a_elems;          // doubles reserved for the working matrix / EPG scratch per warp
+  int copy_elems;       // doubles per TMA bulk copy of one nTE x nT2 matrix (even)
+  int nseed, maxeval;
+  int fixed_alpha;      // SetFlipAngle given
+  int alpha_provided;   // B1 map in out.alpha
+  int epg_kmax;         // highest phase state index + 2
+  int has_part, sp_lo, sp_hi, mp_lo, mp_hi, has_sigmoid;
+  int8_t seeds[DECAES_MAX_ANGLES];
+  double TE, T1, Threshold, Chi2Factor, NoiseLevel, SetFlipAngle, E1;
+  // volume
+  const double *image;
+  long long nvox, stride;
+  // outputs (device pointers, may be null)
+  double *gdn, *ggm, *gva, *fnr, *snr, *alpha, *dist, *resnorm, *decaycurve, *mu, *chi2factor, *decaybasis;
+  double *sfr, *sgm, *mfr, *mgm;
+  // tables
+  const double *basis_rm;   // [nA][copy_elems]  row-major, leading dimension ld (TMA source)
+  const double *basis_cm;   // [nA][nT2][nTE]
+  const double *dbasis_cm;  // [nA][nT2][nTE]   d/d(alpha in degrees)
+  double angles[DECAES_MAX_ANGLES];                            // flip-angle grid (degrees)
+  double logT2[DECAES_MAX_NT2], E2[DECAES_MAX_NT2];            // log(T2_j), exp(-(TE/2)/T2_j)
+  double weights[DECAES_MAX_NT2];                              // sigmoid weights (has_sigmoid)
+  // scratch + scheduling
+  double *scratch;          // per-warp global scratch
+  long long scratch_per_warp;
+  unsigned long long *counters;  // [0] work counter, [1] voxels processed, [2] early returns, [3] lcurve overflow
+};
+
+// layout of the per-warp global scratch (in doubles)
+struct ScratchLayout {
+  int pristine, slots_x, lc_pts, lc_states, fa_u, fa_du, gcv_gamma, gcv_mat, total;
+  __host__ __device__ ScratchLayout(int nTE, int nT2, int copy_elems, bool gcv) {
+    int o = 0;
+    pristine = o, o += copy_elems;
+    slots_x = o, o += DECAES_NCACHE * nT2;
+    lc_pts = o, o += DECAES_LC_MAX * 4;
+    lc_states = o, o += DECAES_LC_MAX * 6;
+    fa_u = o, o += DECAES_MAX_ANGLES;
+    fa_du = o, o += DECAES_MAX_ANGLES;
+    gcv_gamma = o, o += (nTE < nT2 ? nTE : nT2);
+    gcv_mat = o, o += gcv ? nTE * nT2 : 0;
+    total = (o + 1) & ~1;
+  }
+};
+
+// per-warp shared memory layout (in doubles, then ints)
+struct SmemLayout {
+  int A, b, u, x, w, bd, sig, fit, slot_mu, slot_r2, slot_x2, idx, bar, total_bytes;
+  __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems) {
+    int o = 0;
+    A = o, o += a_elems;
+    b = o, o += rows_alloc;
+    u = o, o += rows_alloc;
+    x = o, o += nT2;
+    w = o, o += nT2;
+    bd = o, o += nTE;
+    sig = o, o += DECAES_GROUP * nTE;
+    fit = o, o += nTE;
+    slot_mu = o, o += DECAES_NCACHE;
+    slot_r2 = o, o += DECAES_NCACHE;
+    slot_x2 = o, o += DECAES_NCACHE;
+    bar = o, o += 2;
+    idx = o, o += (nT2 + 1) / 2;
+    total_bytes = ((o * 8) + 15) & ~15;
+  }
+};
+
+struct Warp {
+  const PipeParams &P;
+  NnlsWs ws;
+  double *bd, *sig, *fit, *slot_mu, *slot_r2, *slot_x2;
+  uint64_t *bar;
+  unsigned phase;
+  double *g;  // global scratch of this warp
+  ScratchLayout sl;
+  int dirty_rows;   // lambda rows of the working matrix that may be non-zero
+  int cur_slot;     // 0-based current cache slot (persists across voxels like work.idx[])
+  int lane;
+  unsigned long long n_early, n_overflow;
+
+  __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
+      : P(p), sl(p.nTE, p.nT2, p.copy_elems, p.reg == 2) {
+    SmemLayout L(p.nTE, p.nT2, p.rows_alloc, p.a_elems);
+    ws.A = smem + L.A, ws.b = smem + L.b, ws.u = smem + L.u, ws.x = smem + L.x, ws.w = smem + L.w;
+    ws.idx = (int *)(smem + L.idx);
+    ws.ld = p.ld, ws.n = p.nT2, ws.m0 = p.nTE;
+    bd = smem + L.bd, sig = smem + L.sig, fit = smem + L.fit;
+    slot_mu = smem + L.slot_mu, slot_r2 = smem + L.slot_r2, slot_x2 = smem + L.slot_x2;
+    bar = (uint64_t *)(smem + L.bar);
+    phase = 0;
+    g = gscratch;
+    dirty_rows = p.rows_alloc - p.nTE;
+    cur_slot = 0;
+    lane = lane_id();
+    n_early = n_overflow = 0;
+  }
+
+  // ---- TMA: stage one nTE x nT2 matrix (row-major, ld) from global into the working matrix ----
+  __device__ __noinline__ void stage_matrix(const double *src) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_expect_tx(bar, (unsigned)(P.copy_elems * 8));
+      tma_bulk_g2s(ws.A, src, (unsigned)(P.copy_elems * 8), bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+  }
+
+  // ================= flip-angle fit =================
+  // loss_with_grad!  src/splines.jl:1010-1041
+  __device__ __noinline__ void fa_eval(int k, double &u, double &du) {
+    stage_matrix(P.basis_rm + (size_t)k * P.copy_elems);
+    nnls_warm_start<false>(ws, bd, 0.0, 0);
+    NnlsOut o = nnls_core<false>(ws, 0.0);
+    u = o.rnorm_sq;
+    const double *Ak = P.basis_cm + (size_t)k * P.nTE * P.nT2;
+    const double *dAk = P.dbasis_cm + (size_t)k * P.nTE * P.nT2;
+    double acc = 0.0;
+    for (int i = lane; i < P.nTE; i += 32) {
+      double ax = 0.0, dax = 0.0;
+      for (int j = 0; j < P.nT2; j++) {
+        double xj = ws.x[j];
+        if (xj > 0.0) {
+          ax = fma(xj, Ak[j * P.nTE + i], ax);
+          dax = fma(xj, dAk[j * P.nTE + i], dax);
+        }
+      }
+      acc = fma(dax, ax - bd[i], acc);
+    }
+    du = 2.0 * warp_sum(acc);
+  }
+
+  // CubicHermiteInterpolator + minimize  src/splines.jl:62-110
+  __device__ __noinline__ static void hermite_minimize(double a, double b, double u0, double u1, double m0, double m1,
+                                          double &xo, double &uo) {
+    double r = (b - a) / 2;
+    m0 = __dmul_rn(r, m0), m1 = __dmul_rn(r, m1);
+    double du = u1 - u0, dm = m1 - m0, su = u1 + u0, sm = m1 + m0;
+    double c0 = __dsub_rn(su / 2, dm / 4), c1 = __dsub_rn(__dmul_rn(3.0, du), sm) / 4, c2 = dm / 4, c3 = (sm - du) / 4;
+    double xend = (u0 < u1) ? a : b, uend = (u0 < u1) ? u0 : u1;
+    double D = __dmul_rn(3.0, u0 - u1);
+    double th = __dadd_rn(D / 2, m0 + m1);
+    double gg = __dsub_rn(__dmul_rn(th, th), __dmul_rn(m0, m1));
+    gg = gg > 0 ? -sqrt(gg) : 0.0;
+    double p = -__dadd_rn(D, m0 + m1);
+    double q = __dadd_rn(__dmul_rn(2.0, gg), m0 - m1);
+    xo = xend, uo = uend;
+    if (fabs(p) < fabs(q)) {
+      double t = p / q;
+      double y = fma(t, fma(t, fma(t, c3, c2), c1), c0);
+      if (y < uend) {
+        double c = (a + b) / 2, rr = (b - a) / 2;
+        double x = fma(rr, t, c);
+        x = x < a ? a : (x > b ? b : x);
+        xo = x, uo = y;
+      }
+    }
+  }
+
+  // suggest_point  src/splines.jl:544-566.  Pieces are evaluated in parallel (lane <-> piece);
+  // "first strictly smaller wins" of the sequential scan = lexicographic min over (value, order).
+  __device__ __noinline__ void suggest_point(unsigned long long seen, double &xs, double &us) {
+    const double *fu = g + sl.fa_u, *fdu = g + sl.fa_du;
+    int npts = __popcll(seen);
+    double bestu = CUDART_INF, bestx = 0.0;
+    int besto = 0x7fffffff;
+    // piece t connects the t-th and (t+1)-th probed node; order -1 is the first node itself
+    for (int t = lane - 1; t < npts - 1; t += 32) {
+      double x_, u_;
+      if (t < 0) {
+        int I0 = __ffsll((long long)seen) - 1;
+        x_ = P.angles[I0], u_ = fu[I0];
+      } else {
+        // indices of the t-th and (t+1)-th set bits
+        unsigned long long msk = seen;
+        for (int s = 0; s < t; s++) msk &= msk - 1;
+        int Ia = __ffsll((long long)msk) - 1;
+        msk &= msk - 1;
+        int Ib = __ffsll((long long)msk) - 1;
+        hermite_minimize(P.angles[Ia], P.angles[Ib], fu[Ia], fu[Ib], fdu[Ia], fdu[Ib], x_, u_);
+      }
+      int ord = t + 1;
+      // sequential semantics: the seed node always starts the scan; later candidates replace the
+      // current best only when strictly smaller (NaN never replaces)
+      bool better = (besto == 0x7fffffff) ? (ord == 0 || u_ == u_) : (u_ < bestu);
+      if (better) bestu = u_, bestx = x_, besto = ord;
+    }
+    // warp reduction: smaller value wins, ties -> smaller order; NaN loses (except as the seed)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ou = __shfl_xor_sync(DECAES_FULL_MASK, bestu, o);
+      double ox = __shfl_xor_sync(DECAES_FULL_MASK, bestx, o);
+      int oo = __shfl_xor_sync(DECAES_FULL_MASK, besto, o);
+      bool take = (oo != 0x7fffffff) && (besto == 0x7fffffff || ou < bestu || (ou == bestu && oo < besto));
+      if (take) bestu = ou, bestx = ox, besto = oo;
+    }
+    xs = warp_bcast(bestx, 0), us = warp_bcast(bestu, 0);
+  }
+
+  __device__ void fa_probe(int I, unsigned long long &seen, int &numeval) {
+    double u, du;
+    fa_eval(I, u, du);
+    if (lane == 0) g[sl.fa_u + I] = u, g[sl.fa_du + I] = du;
+    __syncwarp();
+    seen |= (1ull << I);
+    numeval++;
+  }
+
+  // DiscreteSurrogateSearcher + bisection_search  src/splines.jl:705-850 (D = 1).  The seed order
+  // produced by initialize! depends only on (nRefAngles, nRefAnglesMin) and is computed on the host.
+  __device__ __noinline__ double optimize_flip_angle() {
+    unsigned long long seen = 0ull;
+    int numeval = 0;
+    const int maxeval = P.maxeval, nA = P.nA;
+    for (int s = 0; s < P.nseed; s++) fa_probe(P.seeds[s], seen, numeval);
+    double x, u;
+    suggest_point(seen, x, u);
+    while (true) {
+      // minimal_bounding_box :778-800
+      int lo = 0, hi = nA - 1;
+      while (true) {
+        int mid = (lo + hi) / 2;
+        bool in_left = (P.angles[lo] <= x) && (x <= P.angles[mid]);
+        int plo = in_left ? lo : mid, phi = in_left ? mid : hi;
+        bool evaluated = ((seen >> plo) & 1ull) && ((seen >> phi) & 1ull);
+        lo = plo, hi = phi;
+        if (!evaluated || !(hi - lo > 1)) break;
+      }
+      // evaluate_box! :802-815 with corners sorted by distance to x (stable)
+      {
+        double d0 = __dmul_rn(P.angles[lo] - x, P.angles[lo] - x), d1 = __dmul_rn(P.angles[hi] - x, P.angles[hi] - x);
+        int c0 = lo, c1 = hi;
+        if (d1 < d0) c0 = hi, c1 = lo;
+        int cs[2] = {c0, c1};
+        for (int k = 0; k < 2; k++) {
+          if (((seen >> lo) & 1ull) && ((seen >> hi) & 1ull)) break;
+          if (numeval >= maxeval) break;
+          if ((seen >> cs[k]) & 1ull) continue;
+          fa_probe(cs[k], seen, numeval);
+          if (numeval >= maxeval) break;
+        }
+      }
+      suggest_point(seen, x, u);
+      if (numeval >= maxeval || (hi - lo) <= 1) break;
+    }
+    return x;
+  }
+
+  // ================= EPG basis at the fitted angle =================
+  // lane <-> T2 component; phase states of each lane's curve live in shared memory (the working
+  // matrix region is free at this point), updated in place.  Arithmetic follows
+  // epg_impulse_response! src/EPGdecaycurve.jl:948-1028 operation by operation.
+  __device__ __noinline__ void epg_basis(double alpha_deg, long long v) {
+    const int ETL = P.nTE, n = P.nT2, ld = P.ld;
+    double *S = ws.A;  // [3][K][32]
+    const int K = P.epg_kmax;
+    double *pr = g + sl.pristine;
+    double sina, cosa;
+    sincos(alpha_deg * 0.017453292519943295, &sina, &cosa);
+    const double m0 = sind_0_180(alpha_deg / 2);
+    const double E1 = P.E1;
+#define ST(c, k) S[((c)*K + (k)) * 32 + lane]
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const bool act = j < n;
+      const double E2 = act ? P.E2[j] : 0.0;
+      const double E2h = __dmul_rn(E2, E2) / 2, E1E2 = __dmul_rn(E1, E2), E1sq = __dmul_rn(E1, E1);
+      const double a = E2h, b = __dmul_rn(E2h, cosa), c = __dmul_rn(E1E2, sina), d = __dmul_rn(E1sq, cosa);
+      const double cp = -c / 2;
+      double F, Fb, Z, C, Sd, Cp, Sp, vF, vFb, vZ;
+#define UPD()                                   \
+  C = __dadd_rn(F, Fb), Sd = __dsub_rn(F, Fb);  \
+  Cp = __dmul_rn(a, C), Sp = __dmul_rn(b, Sd);  \
+  vFb = fma(-c, Z, __dsub_rn(Cp, Sp));          \
+  vF = fma(c, Z, __dadd_rn(Cp, Sp));            \
+  vZ = fma(cp, Sd, __dmul_rn(d, Z))
+      double dc = __dsub_rn(a, b);
+      if (act) pr[0 * ld + j] = fabs(__dmul_rn(m0, dc));
+      ST(0, 1) = __dsub_rn(a, b), ST(1, 1) = 0.0, ST(2, 1) = cp;
+      ST(0, 2) = __dadd_rn(a, b), ST(1, 2) = 0.0, ST(2, 2) = 0.0;
+      for (int i = 2; i <= ETL - 1; i++) {
+        const bool first_half = (i <= ETL / 2);
+        const int kmax = first_half ? i : ETL - i + 1;
+        F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
+        UPD();
+        if (act) pr[(i - 1) * ld + j] = fabs(__dmul_rn(m0, vFb));
+        ST(0, 1) = vFb, ST(2, 1) = vZ;
+        double pend = vF;
+        for (int k = 2; k <= kmax; k++) {
+          F = ST(0, k), Fb = ST(1, k), Z = ST(2, k);
+          ST(0, k) = pend;
+          UPD();
+          pend = vF;
+          ST(1, k - 1) = vFb;
+          ST(2, k) = vZ;
+        }
+        ST(0, kmax + 1) = pend;
+        if (first_half) ST(1, i) = 0.0, ST(1, i + 1) = 0.0, ST(2, i + 1) = 0.0;
+      }
+      F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
+      C = __dadd_rn(F, Fb), Sd = __dsub_rn(F, Fb);
+      dc = fma(-c, Z, fma(a, C, __dmul_rn(-b, Sd)));
+      if (act) pr[(ETL - 1) * ld + j] = fabs(__dmul_rn(m0, dc));
+    }
+#undef ST
+#undef UPD
+    dirty_rows = P.rows_alloc - P.nTE;  // the scratch overlapped the lambda rows
+    if (P.decaybasis && !P.fixed_alpha) {
+      __syncwarp();
+      for (int k = lane; k < ETL * n; k += 32) {
+        int i = k % ETL, jj = k / ETL;
+        P.decaybasis[v + (long long)k * P.stride] = pr[i * ld + jj];
+      }
+    }
+    __threadfence_block();
+    __syncwarp();
+  }
+
+  // ================= regularised solves =================
+  __device__ __noinline__ NnlsOut solve_unreg(const double *Asrc) {
+    stage_matrix(Asrc);
+    nnls_warm_start<false>(ws, bd, 0.0, 0);
+    return nnls_core<false>(ws, 0.0);
+  }
+
+  // solve!(cache, mu)  src/lsqnonneg.jl:417-444 — exact-mu hit or solve into the next slot
+  __device__ void cache_reset() {
+    if (lane < DECAES_NCACHE) slot_mu[lane] = CUDART_NAN;
+    __syncwarp();
+  }
+  __device__ __noinline__ void cache_solve(double mu, const double *Asrc) {
+    int hit = -1, firstnan = -1;
+    for (int i = 0; i < DECAES_NCACHE; i++) {
+      double mui = slot_mu[i];
+      if (isnan(mui)) {
+        if (firstnan < 0) firstnan = i;
+      } else if (mu == mui) {
+        hit = i;
+        break;
+      }
+    }
+    if (hit >= 0) {
+      cur_slot = hit;
+      return;
+    }
+    cur_slot = (firstnan >= 0) ? firstnan : (cur_slot + 1) % DECAES_NCACHE;
+    stage_matrix(Asrc);
+    nnls_warm_start<true>(ws, bd, mu, dirty_rows);
+    NnlsOut o = nnls_core<true>(ws, mu);
+    dirty_rows = o.rows_used - P.nTE;
+    double *sx = g + sl.slots_x + cur_slot * P.nT2;
+    for (int j = lane; j < P.nT2; j += 32) sx[j] = ws.x[j];
+    if (lane == 0) slot_mu[cur_slot] = mu, slot_r2[cur_slot] = o.rnorm_sq, slot_x2[cur_slot] = o.xnorm_sq;
+    __syncwarp();
+  }
+  __device__ __forceinline__ double cur_seminorm_sq() const { return slot_x2[cur_slot]; }
+  __device__ __forceinline__ double cur_resnorm_sq() const {  // src/lsqnonneg.jl:309-313
+    double mu = slot_mu[cur_slot];
+    double r = slot_r2[cur_slot] - __dmul_rn(__dmul_rn(mu, mu), slot_x2[cur_slot]);
+    return r > 0 ? r : 0.0;
+  }
+
+  // ---- L-curve  src/lsqnonneg.jl:812-972 ----
+  static __device__ __forceinline__ bool isapprox(double x, double y) {
+    if (x == y) return true;
+    if (!isfinite(x) || !isfinite(y)) return false;
+    return fabs(x - y) <= 1.4901161193847656e-08 * fmax(fabs(x), fabs(y));
+  }
+  static __device__ __forceinline__ bool isless_f(double a, double b) {
+    if (isnan(a)) return false;
+    if (isnan(b)) return true;
+    if (a == 0 && b == 0) return signbit(a) && !signbit(b);
+    return a < b;
+  }
+  static __device__ __forceinline__ double norm2(double ax, double ay, double bx, double by) {
+    double dx = ax - bx, dy = ay - by;
+    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  }
+  static __device__ double menger(double jx, double jy, double kx, double ky, double lx, double ly) {
+    double jk0 = jx - kx, jk1 = jy - ky, kl0 = kx - lx, kl1 = ky - ly, lj0 = lx - jx, lj1 = ly - jy;
+    double d1 = __dadd_rn(__dmul_rn(jk0, jk0), __dmul_rn(jk1, jk1));
+    double d2 = __dadd_rn(__dmul_rn(kl0, kl0), __dmul_rn(kl1, kl1));
+    double d3 = __dadd_rn(__dmul_rn(lj0, lj0), __dmul_rn(lj1, lj1));
+    double cr = __dsub_rn(__dmul_rn(jk0, kl1), __dmul_rn(jk1, kl0));
+    return __dmul_rn(2.0, cr) / sqrt(__dmul_rn(__dmul_rn(d1, d2), d3));
+  }
+
+  // cached evaluation of P(t) = (log ||Ax-b||^2, log ||x||^2); returns the point-cache index
+  __device__ __noinline__ int lc_eval(double t, int &npts, const double *Asrc) {
+    double *pts = g + sl.lc_pts;
+    for (int i = 0; i < npts; i++)
+      if (isapprox(t, pts[4 * i])) return i;
+    cache_solve(exp(t), Asrc);
+    double xi = log(cur_resnorm_sq()), eta = log(cur_seminorm_sq());
+    int i = npts;
+    if (npts < DECAES_LC_MAX) {
+      if (lane == 0) pts[4 * i] = t, pts[4 * i + 1] = xi, pts[4 * i + 2] = eta, pts[4 * i + 3] = -CUDART_INF;
+      npts++;
+    } else {
+      i = DECAES_LC_MAX - 1;
+      n_overflow++;
+    }
+    __syncwarp();
+    return i;
+  }
+
+  __device__ __noinline__ void lc_update_curvature(const double *sx, const int *si, int npts, double tlx, double tly, double brx,
+                                      double bry, double Ctol) {
+    double *pts = g + sl.lc_pts;
+    for (int q = 0; q < 4; q++) {
+      int pi = si[q];
+      double x = sx[q], px = pts[4 * pi + 1], py = pts[4 * pi + 2];
+      double C = -CUDART_INF;
+      if (fmin(norm2(px, py, tlx, tly), norm2(px, py, brx, bry)) > Ctol) {
+        double xm = -CUDART_INF, xp = CUDART_INF, mx = px, my = py, qx = px, qy = py;
+        for (int k = 0; k < npts; k++) {
+          double _x = pts[4 * k];
+          if (xm < _x && _x < x) xm = _x, mx = pts[4 * k + 1], my = pts[4 * k + 2];
+          if (x < _x && _x < xp) xp = _x, qx = pts[4 * k + 1], qy = pts[4 * k + 2];
+        }
+        C = menger(mx, my, px, py, qx, qy);
+      }
+      __syncwarp();
+      if (lane == 0) pts[4 * pi + 3] = C;
+      __syncwarp();
+    }
+  }
+
+  __device__ int lc_argmax(int npts) {
+    const double *pts = g + sl.lc_pts;
+    int best = 0;
+    for (int i = 1; i < npts; i++)
+      if (isless_f(pts[4 * best + 3], pts[4 * i + 3])) best = i;
+    return best;
+  }
+
+  __device__ __noinline__ double lcurve_corner(const double *Asrc) {
+    const double phi = 1.618033988749895, xtol = 1e-4, Ptol = 1e-4, Ctol = 1e-4;
+    double *pts = g + sl.lc_pts, *sts = g + sl.lc_states;
+    int npts = 0, nst = 0;
+    double sx[4];
+    int si[4];
+    sx[0] = -8.0, sx[3] = 2.0;
+    sx[1] = __dadd_rn(__dmul_rn(phi, sx[0]), sx[3]) / (phi + 1);
+    sx[2] = sx[0] + (sx[3] - sx[1]);
+    for (int q = 0; q < 4; q++) si[q] = lc_eval(sx[q], npts, Asrc);
+    const double tlx = pts[4 * si[0] + 1], tly = pts[4 * si[0] + 2], brx = pts[4 * si[3] + 1], bry = pts[4 * si[3] + 2];
+    lc_update_curvature(sx, si, npts, tlx, tly, brx, bry, Ctol);
+    int iter = 0;
+    while (true) {
+      double p1x = pts[4 * si[0] + 1], p1y = pts[4 * si[0] + 2], p4x = pts[4 * si[3] + 1], p4y = pts[4 * si[3] + 2];
+      if (fabs(sx[3] - sx[0]) < xtol || norm2(p1x, p1y, p4x, p4y) < Ptol) break;
+      iter++;
+      {  // backtracking  :892-900
+        double xb = pts[4 * lc_argmax(npts)];
+        for (int k = 0; k < nst; k++) {
+          const double *s = sts + 6 * k;
+          if ((s[1] == xb || s[2] == xb) && fabs(s[3] - s[0]) <= fabs(sx[3] - sx[0])) {
+            unsigned long long packed = (unsigned long long)__double_as_longlong(s[4]);
+            for (int q = 0; q < 4; q++) sx[q] = s[q], si[q] = (int)((packed >> (16 * q)) & 0xffff);
+          }
+        }
+      }
+      double C2 = pts[4 * si[1] + 3], C3 = pts[4 * si[2] + 3];
+      if (C2 > C3) {  // move_left  :933-939
+        double nx = __dadd_rn(__dmul_rn(phi, sx[0]), sx[2]) / (phi + 1);
+        sx[3] = sx[2], si[3] = si[2];
+        sx[2] = sx[1], si[2] = si[1];
+        sx[1] = nx;
+        si[1] = lc_eval(nx, npts, Asrc);
+      } else {  // move_right  :941-946
+        double nx = sx[1] + (sx[3] - sx[2]);
+        sx[0] = sx[1], si[0] = si[1];
+        sx[1] = sx[2], si[1] = si[2];
+        sx[2] = nx;
+        si[2] = lc_eval(nx, npts, Asrc);
+      }
+      lc_update_curvature(sx, si, npts, tlx, tly, brx, bry, Ctol);
+      if (nst < DECAES_LC_MAX) {
+        if (lane == 0) {
+          double *s = sts + 6 * nst;
+          unsigned long long packed = 0ull;
+          for (int q = 0; q < 4; q++) s[q] = sx[q], packed |= ((unsigned long long)si[q]) << (16 * q);
+          s[4] = __longlong_as_double((long long)packed);
+          s[5] = (double)iter;
+        }
+        nst++;
+        __syncwarp();
+      } else {
+        n_overflow++;
+        break;
+      }
+    }
+    return pts[4 * lc_argmax(npts)];
+  }
+
+  // ---- Brent root / bracket (src/optimization.jl:71-128, 177-219) on f(log mu) ----
+  // mode 0: chi2 relative error (src/lsqnonneg.jl:374-385); mode 1: res^2 - delta^2 (:723-726)
+  __device__ double root_fun(double logmu, double target, int mode, const double *Asrc) {
+    cache_solve(exp(logmu), Asrc);
+    double r2 = cur_resnorm_sq();
+    return mode == 0 ? (r2 - target) / target : r2 - target;
+  }
+  static __device__ __forceinline__ double sgn(double x) { return (double)((x > 0) - (x < 0)); }
+
+  __device__ __noinline__ void bracket_and_brent(double target, int mode, double ftol, const double *Asrc, double &x_final,
+                                    double &f_final) {
+    // bracket_root_monotonic(f, -4, 1; dilate = 1.5, mono = +1, maxiters = 6)
+    double a = -4.0, delta = 1.0, b, fa, fb;
+    bool bracket_done = false;
+    fa = root_fun(a, target, mode, Asrc);
+    if (!isfinite(fa)) {
+      b = a, fa = CUDART_NAN, fb = CUDART_NAN, bracket_done = true;
+    } else if (fa == 0) {
+      b = a, fb = fa, bracket_done = true;
+    }
+    if (!bracket_done) {
+      double sd = sgn(fa);  // sign(mono) = +1
+      b = a - sd * delta;
+      fb = root_fun(b, target, mode, Asrc);
+      if (!isfinite(fb)) {
+        b = a, fb = fa, bracket_done = true;
+      } else if (fb == 0) {
+        a = b, fa = fb, bracket_done = true;
+      }
+      if (!bracket_done) {
+        delta *= 1.5;
+        int cnt = 0;
+        while (fa * fb > 0 && cnt < 6) {
+          a = b, fa = fb;
+          b = a - sd * delta;
+          fb = root_fun(b, target, mode, Asrc);
+          if (!isfinite(fb)) {
+            b = a, fb = fa, bracket_done = true;
+            break;
+          }
+          if (fb == 0) {
+            a = b, fa = fb, bracket_done = true;
+            break;
+          }
+          delta *= 1.5;
+          cnt++;
+        }
+        if (!bracket_done && !(a < b)) {
+          double t = a;
+          a = b, b = t, t = fa, fa = fb, fb = t;
+        }
+      }
+    }
+    if (fa * fb < 0) {
+      // brent_root(f, a, b, fa, fb; xatol = 0, xrtol = 0, ftol, maxiters = 100)
+      double x0 = a, x1 = b, fx0 = fa, fx1 = fb;
+      double A_ = x0, B_ = x1, fA = fx0, fB = fx1;
+      if (fabs(fA) < fabs(fB)) {
+        double t = A_;
+        A_ = B_, B_ = t, t = fA, fA = fB, fB = t;
+      }
+      double c = x0, d = x0, fc = fx0;
+      bool mflag = true;
+      x_final = B_, f_final = fB;
+      bool done = false;
+      for (int it = 1; it <= 100 && !done; it++) {
+        if (fabs(B_ - A_) <= 0.0) break;
+        double s = 0.0;
+        s += A_ * fB * fc / (fA - fB) / (fA - fc);
+        s += B_ * fA * fc / (fB - fA) / (fB - fc);
+        s += c * fA * fB / (fc - fA) / (fc - fB);
+        if (isnan(s) || isinf(s)) s = A_ - fA * (B_ - A_) / (fB - fA);
+        double uu = (3 * A_ + B_) / 4, vv = B_;
+        if (uu > vv) {
+          double t = uu;
+          uu = vv, vv = t;
+        }
+        double tol = 0.0;  // max(xatol, xrtol * ...) with both zero
+        if (!(uu < s && s < vv) || (mflag && fabs(s - B_) >= fabs(B_ - c) / 2) ||
+            (!mflag && fabs(s - B_) >= fabs(B_ - c) / 2) || (mflag && fabs(B_ - c) <= tol) ||
+            (!mflag && fabs(c - d) <= tol)) {
+          s = (A_ + B_) / 2;
+          mflag = true;
+        } else {
+          mflag = false;
+        }
+        double fs = root_fun(s, target, mode, Asrc);
+        if (fs == 0) {
+          x_final = s, f_final = fs, done = true;
+          break;
+        }
+        if (isnan(fs) || isinf(fs)) break;
+        if (fabs(fs) <= ftol) {
+          x_final = s, f_final = fs, done = true;
+          break;
+        }
+        d = c, c = B_, fc = fB;
+        if (sgn(fA) * sgn(fs) < 0)
+          B_ = s, fB = fs;
+        else
+          A_ = s, fA = fs;
+        if (fabs(fA) < fabs(fB)) {
+          double t = A_;
+          A_ = B_, B_ = t, t = fA, fA = fB, fB = t;
+        }
+        x_final = B_, f_final = fB;
+      }
+    } else {
+      if (!isfinite(fa))
+        x_final = b, f_final = fb;
+      else if (!isfinite(fb))
+        x_final = a, f_final = fa;
+      else if (fabs(fa) < fabs(fb))
+        x_final = a, f_final = fa;
+      else
+        x_final = b, f_final = fb;
+    }
+  }
+
+  // ---- GCV  src/lsqnonneg.jl:1136-1205 ----
+  // singular values of the voxel's basis by one-sided Jacobi on the smaller Gram-free side
+  // (stands in for LAPACK dgesdd_, src/utils.jl:103-134).  lane <-> element of a column pair.
+  __device__ __noinline__ void gcv_svdvals(const double *Asrc) {
+    const int m = P.nTE, n = P.nT2, ld = P.ld;
+    double *Gm = g + sl.gcv_mat;  // tall r x c, column-major
+    const int r = m >= n ? m : n, c = m >= n ? n : m;
+    for (int k = lane; k < m * n; k += 32) {
+      int i = k % m, j = k / m;
+      double v = Asrc[i * ld + j];
+      if (m >= n) Gm[i + j * r] = v; else Gm[j + i * r] = v;
+    }
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; sweep++) {
+      bool rotated = false;
+      for (int p = 0; p < c - 1; p++)
+        for (int q = p + 1; q < c; q++) {
+          double *gp = Gm + p * r, *gq = Gm + q * r;
+          double al = 0, be = 0, ga = 0;
+          for (int i = lane; i < r; i += 32) {
+            double up = gp[i], uq = gq[i];
+            al = fma(up, up, al), be = fma(uq, uq, be), ga = fma(up, uq, ga);
+          }
+          al = warp_sum(al), be = warp_sum(be), ga = warp_sum(ga);
+          if (ga == 0.0 || fabs(ga) <= DBL_EPSILON * sqrt(al * be)) continue;
+          rotated = true;
+          double zeta = (be - al) / (2 * ga);
+          double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+          double cs = 1 / sqrt(1 + t * t), sn = cs * t;
+          for (int i = lane; i < r; i += 32) {
+            double up = gp[i], uq = gq[i];
+            gp[i] = cs * up - sn * uq;
+            gq[i] = sn * up + cs * uq;
+          }
+          __syncwarp();
+        }
+      if (!rotated) break;
+    }
+    double *gam = g + sl.gcv_gamma;
+    for (int j = 0; j < c; j++) {
+      double s = 0;
+      for (int i = lane; i < r; i += 32) s = fma(Gm[j * r + i], Gm[j * r + i], s);
+      s = warp_sum(s);
+      if (lane == 0) gam[j] = sqrt(s);
+    }
+    __syncwarp();
+  }
+  __device__ __noinline__ double gcv_fun(double logmu, const double *Asrc) {  // log(max(gcv, eps^2/m))  :1150-1154, 1213-1229
+    const int m = P.nTE, n = P.nT2;
+    double mu = exp(logmu);
+    cache_solve(mu, Asrc);
+    double r2 = cur_resnorm_sq();
+    double dof = (double)((m - n) > 0 ? (m - n) : 0);
+    double l2 = __dmul_rn(mu, mu);
+    const double *gam = g + sl.gcv_gamma;
+    int mn = m < n ? m : n;
+    for (int i = 0; i < mn; i++) {
+      double g2 = __dmul_rn(gam[i], gam[i]);
+      dof += l2 / (g2 + l2);
+    }
+    double gcv = r2 / __dmul_rn(dof, dof);
+    gcv = fmax(gcv, (DBL_EPSILON * DBL_EPSILON) / m);
+    return log(gcv);
+  }
+  __device__ __noinline__ double gcv_minimize(const double *Asrc) {  // brent_minimize  src/optimization.jl:319-413
+    const double phi = 1.618033988749895, alpha = 2 - phi, xatol = 1e-4;
+    double x1 = -8.0, x2 = 2.0;
+    double x = x1 + alpha * (x2 - x1);
+    double y = gcv_fun(x, Asrc);
+    double dx_old = 0.0, dx = 0.0, x_older = x, x_old = x, y_older = y, y_old = y;
+    int iter = 0;
+    while (iter < 20) {
+      double p = 0.0, q = 0.0, xm = (x2 + x1) / 2;
+      double dx_tol = xatol;  // + xrtol * |x| with xrtol = 0
+      if (fabs(x - xm) + (x2 - x1) / 2 <= 2 * dx_tol) break;
+      iter++;
+      if (fabs(dx_old) > dx_tol) {
+        double r = __dmul_rn(x - x_old, y - y_older);
+        q = __dmul_rn(x - x_older, y - y_old);
+        p = __dsub_rn(__dmul_rn(x - x_older, q), __dmul_rn(x - x_old, r));
+        q = 2 * (q - r);
+        if (q > 0) p = -p; else q = -q;
+      }
+      if (fabs(p) < fabs(q * dx_old / 2) && p < q * (x2 - x) && p < q * (x - x1)) {
+        dx_old = dx;
+        dx = p / q;
+        double x_tmp = x + dx;
+        if ((x_tmp - x1) < 2 * dx_tol || (x2 - x_tmp) < 2 * dx_tol) dx = (x < xm) ? dx_tol : -dx_tol;
+      } else {
+        dx_old = (x < xm) ? x2 - x : x1 - x;
+        dx = __dmul_rn(alpha, dx_old);
+      }
+      double x_new = (fabs(dx) >= dx_tol) ? x + dx : x + ((dx > 0) ? dx_tol : -dx_tol);
+      double y_new = gcv_fun(x_new, Asrc);
+      if (y_new < y) {
+        if (x_new < x) x2 = x; else x1 = x;
+        x_older = x_old, x_old = x, x = x_new;
+        y_older = y_old, y_old = y, y = y_new;
+      } else {
+        if (x_new < x) x1 = x_new; else x2 = x_new;
+        if (y_new <= y_old || x_old == x) {
+          x_older = x_old, x_old = x_new, y_older = y_old, y_old = y_new;
+        } else if (y_new <= y_older || x_older == x || x_older == x_old) {
+          x_older = x_new, y_older = y_new;
+        }
+      }
+    }
+    return x;
+  }
+
+  // ================= one voxel =================
+  __device__ __noinline__ void process(long long v, const double *signal /* smem, nTE */) {
+    const int nTE = P.nTE, n = P.nT2;
+    // normalise  src/T2mapSEcorr.jl:205-218
+    double mx = 0.0;
+    for (int i = lane; i < nTE; i += 32) {
+      double bi = signal[i];
+      mx = bi > mx ? bi : mx;
+    }
+    const double max_signal = warp_max(mx);
+    for (int i = lane; i < nTE; i += 32) bd[i] = (max_signal > 0) ? signal[i] / max_signal : signal[i];
+    __syncwarp();
+
+    // flip angle + basis
+    double alpha;
+    const double *Asrc;
+    if (P.alpha_provided) {
+      alpha = P.alpha[v];
+      epg_basis(alpha, v);
+      Asrc = g + sl.pristine;
+    } else if (P.fixed_alpha) {
+      alpha = P.SetFlipAngle;
+      Asrc = P.basis_rm;
+    } else {
+      alpha = optimize_flip_angle();
+      epg_basis(alpha, v);
+      Asrc = g + sl.pristine;
+    }
+
+    // T2_distribution!  src/T2mapSEcorr.jl:475-505
+    double mu = CUDART_NAN, chi2 = CUDART_NAN;
+    int src_kind = 0;  // 0: ws.x (unregularised solve just done), 1: cache slot, 2: zeros
+    const bool want_chi2 = (P.chi2factor != nullptr);
+    switch (P.reg) {
+      case 0: {
+        mu = 0.0, chi2 = 1.0;
+        solve_unreg(Asrc);
+      } break;
+      case 1: {  // lsqnonneg_lcurve!  src/lsqnonneg.jl:812-840
+        cache_reset();
+        double logmu = lcurve_corner(Asrc);
+        mu = exp(logmu);
+        cache_solve(mu, Asrc);
+        src_kind = 1;
+        if (want_chi2) {  // the unregularised solve only feeds chi2factor
+          double r2 = cur_resnorm_sq();
+          NnlsOut o = solve_unreg(Asrc);
+          chi2 = r2 / o.rnorm_sq;
+        }
+      } break;
+      case 2: {  // lsqnonneg_gcv!  src/lsqnonneg.jl:1136-1205
+        gcv_svdvals(Asrc);
+        cache_reset();
+        double logmu = gcv_minimize(Asrc);
+        mu = exp(logmu);
+        cache_solve(mu, Asrc);
+        src_kind = 1;
+        if (want_chi2) {
+          double r2 = cur_resnorm_sq();
+          NnlsOut o = solve_unreg(Asrc);
+          chi2 = r2 / o.rnorm_sq;
+        }
+      } break;
+      case 3:    // lsqnonneg_chi2!  src/lsqnonneg.jl:504-593
+      case 4: {  // lsqnonneg_mdp!   src/lsqnonneg.jl:700-747
+        NnlsOut o = solve_unreg(Asrc);
+        double res2_min = o.rnorm_sq;
+        bool early = false;
+        double target, ftol;
+        int mode;
+        if (P.reg == 3) {
+          early = (res2_min == 0 || o.nsetp == 0);
+          target = __dmul_rn(P.Chi2Factor, res2_min), ftol = 1e-3 * (P.Chi2Factor - 1), mode = 0;
+          if (early) mu = 0.0, chi2 = 1.0;
+        } else {
+          double sigma = P.NoiseLevel / max_signal;
+          double delta = __dmul_rn(sqrt((double)nTE), sigma);
+          double acc = 0.0;
+          for (int i = lane; i < nTE; i += 32) acc = fma(bd[i], bd[i], acc);
+          double res2_max = warp_sum(acc);
+          target = __dmul_rn(delta, delta), ftol = 1e-3 * target, mode = 1;
+          if (delta <= sqrt(res2_min)) {
+            early = true, mu = 0.0, chi2 = 1.0;
+          } else if (delta >= sqrt(res2_max)) {
+            early = true, mu = CUDART_INF, chi2 = res2_max / res2_min, src_kind = 2;
+          }
+        }
+        if (early) {
+          // the reference's save_results! reads a stale cache slot here (src/lsqnonneg.jl:465, 657);
+          // we return the value the chooser itself returns and count the voxel
+          n_early++;
+        } else {
+          cache_reset();
+          double xf, ff;
+          bracket_and_brent(target, mode, ftol, Asrc, xf, ff);
+          if (isfinite(ff)) {
+            mu = exp(xf);
+            double res2_final = (mode == 0) ? __dmul_rn(target, 1 + ff) : target + ff;
+            cache_solve(mu, Asrc);
+            chi2 = res2_final / res2_min;
+            src_kind = 1;
+          } else {
+            mu = 0.0, chi2 = 1.0 / res2_min;
+            solve_unreg(Asrc);
+          }
+        }
+      } break;
+    }
+
+    // save_results!  src/T2mapSEcorr.jl:512-591
+    double *xs = ws.w;  // dual no longer needed
+    {
+      const double *sx = g + sl.slots_x + cur_slot * n;
+      for (int j = lane; j < n; j += 32) {
+        double xv = (src_kind == 0) ? ws.x[j] : (src_kind == 1 ? sx[j] : 0.0);
+        xs[j] = __dmul_rn(xv, max_signal);
+      }
+    }
+    stage_matrix(Asrc);  // pristine basis back into shared memory for fit = A x
+    double r2 = 0.0, rs = 0.0;
+    for (int i = lane; i < nTE; i += 32) {
+      const double *row = ws.A + i * P.ld;
+      double s = 0.0;
+      for (int j = 0; j < n; j++) s = fma(row[j], xs[j], s);
+      fit[i] = s;
+      double res = s - __dmul_rn(bd[i], max_signal);
+      ws.u[i] = res;
+      r2 = fma(res, res, r2);
+      rs += res;
+    }
+    r2 = warp_sum(r2);
+    double mean = warp_sum(rs) / nTE;
+    double var = 0.0;
+    for (int i = lane; i < nTE; i += 32) {
+      double dlt = ws.u[i] - mean;
+      var = fma(dlt, dlt, var);
+    }
+    var = warp_sum(var);
+    double S = 0.0, dotl = 0.0;
+    for (int j = lane; j < n; j += 32) S += xs[j], dotl = fma(xs[j], P.logT2[j], dotl);
+    S = warp_sum(S), dotl = warp_sum(dotl);
+    double log_ggm = dotl / S;
+    double l1p = 0.0;
+    for (int j = lane; j < n; j += 32) {
+      double dlt = P.logT2[j] - log_ggm;
+      l1p = fma(__dmul_rn(dlt, dlt), xs[j], l1p);
+    }
+    l1p = warp_sum(l1p) / S;
+
+    if (lane == 0) {
+      P.gdn[v] = S;
+      P.ggm[v] = exp(log_ggm);
+      P.gva[v] = expm1(l1p);
+      P.fnr[v] = S / sqrt(r2 / (nTE - 1));
+      P.snr[v] = max_signal / sqrt(var / (nTE - 1));
+      P.alpha[v] = alpha;
+      if (P.mu && P.chi2factor) P.mu[v] = mu, P.chi2factor[v] = chi2;
+      if (P.resnorm) P.resnorm[v] = sqrt(r2);
+    }
+    for (int j = lane; j < n; j += 32) P.dist[v + (long long)j * P.stride] = xs[j];
+    if (P.decaycurve)
+      for (int i = lane; i < nTE; i += 32) P.decaycurve[v + (long long)i * P.stride] = fit[i];
+
+    // fused T2part epilogue  src/T2partSEcorr.jl:95-138
+    if (P.has_part) {
+      bool isn = false;
+      double Ssp = 0, Smp = 0, dsp = 0, dmp = 0, dw = 0;
+      for (int j = lane; j < n; j += 32) {
+        double dj = xs[j];
+        isn |= isnan(dj);
+        if (j >= P.sp_lo && j <= P.sp_hi) dsp += __dmul_rn(dj, P.logT2[j]), Ssp += dj;
+        if (j >= P.mp_lo && j <= P.mp_hi) dmp += __dmul_rn(dj, P.logT2[j]), Smp += dj;
+        if (P.has_sigmoid) dw = fma(dj, P.weights[j], dw);
+      }
+      Ssp = warp_sum(Ssp), Smp = warp_sum(Smp), dsp = warp_sum(dsp), dmp = warp_sum(dmp), dw = warp_sum(dw);
+      const bool anynan = __any_sync(DECAES_FULL_MASK, isn);
+      if (lane == 0) {
+        // entries the reference leaves untouched keep its NaN pre-fill (src/T2partSEcorr.jl:83-90)
+        double sfr = CUDART_NAN, mfr = CUDART_NAN, sgm = CUDART_NAN, mgm = CUDART_NAN;
+        if (!anynan) {
+          if (S > 0) sfr = P.has_sigmoid ? dw / S : Ssp / S, mfr = Smp / S;
+          if (Ssp > 0) sgm = exp(dsp / Ssp);
+          if (Smp > 0) mgm = exp(dmp / Smp);
+        }
+        P.sfr[v] = sfr, P.mfr[v] = mfr, P.sgm[v] = sgm, P.mgm[v] = mgm;
+      }
+    }
+    __syncwarp();
+  }
+};
+
+}  // namespace decaes

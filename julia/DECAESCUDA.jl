@@ -1,0 +1,135 @@
+# DECAESCUDA.jl — reference-side binding for libdecaes_cuda (see INTEGRATION.md).
+#
+# Loading this file after `using DECAES` adds GPU methods that replace the two worker loops
+#   T2mapSEcorr!  : src/T2mapSEcorr.jl:177-193   (voxelwise_T2_distribution! per voxel)
+#   T2partSEcorr  : src/T2partSEcorr.jl:58-68    (voxelwise_T2_parts! per voxel)
+# with one blocking `ccall` each.  Everything before (options, NaN-filled outputs,
+# src/T2mapSEcorr.jl:24-54) and after (Dict / Array conversion, :195) is the reference's own code,
+# so the public API, option structs and output maps are unchanged.
+#
+# NOTE: there is no Julia runtime in the build image, so this file is not exercised by the test
+# suite (tests/test_abi.py only checks that it names every field of the C structs).
+module DECAESCUDA
+
+using DECAES
+using DECAES: T2mapOptions, T2partOptions, T2Maps, T2Distributions, T2Parts, is_B1map_provided
+
+const libdecaes_cuda = get(ENV, "DECAES_CUDA_LIB", "libdecaes_cuda")
+
+# Flat mirrors of include/decaes_cuda.h — field order and types must match exactly.
+struct CT2mapOpts
+    nx::Int32; ny::Int32; nz::Int32
+    nTE::Int32
+    nT2::Int32
+    nRefAngles::Int32
+    nRefAnglesMin::Int32
+    reg::Int32
+    legacy::Int32
+    alpha_provided::Int32
+    ngpus::Int32
+    reserved::Int32
+    TE::Float64
+    T2min::Float64; T2max::Float64
+    T1::Float64
+    Threshold::Float64
+    MinRefAngle::Float64
+    RefConAngle::Float64
+    Chi2Factor::Float64
+    NoiseLevel::Float64
+    SetFlipAngle::Float64
+end
+
+struct CT2partOpts
+    nx::Int32; ny::Int32; nz::Int32
+    nT2::Int32
+    T2min::Float64; T2max::Float64
+    SPWin_lo::Float64; SPWin_hi::Float64
+    MPWin_lo::Float64; MPWin_hi::Float64
+    Sigmoid::Float64
+end
+
+struct CT2mapOut
+    gdn::Ptr{Float64}; ggm::Ptr{Float64}; gva::Ptr{Float64}; fnr::Ptr{Float64}; snr::Ptr{Float64}; alpha::Ptr{Float64}
+    dist::Ptr{Float64}
+    resnorm::Ptr{Float64}
+    decaycurve::Ptr{Float64}
+    mu::Ptr{Float64}; chi2factor::Ptr{Float64}
+    decaybasis::Ptr{Float64}
+    sfr::Ptr{Float64}; sgm::Ptr{Float64}; mfr::Ptr{Float64}; mgm::Ptr{Float64}
+end
+
+const REG_CODES = Dict("none" => 0, "lcurve" => 1, "gcv" => 2, "chi2" => 3, "mdp" => 4)
+nan_if_nothing(x) = x === nothing ? NaN : Float64(x)
+ptr_or_null(x::Nothing) = Ptr{Float64}(C_NULL)
+ptr_or_null(x::Array{Float64}) = pointer(x)
+
+function CT2mapOpts(o::T2mapOptions{Float64}; alpha_provided::Bool, ngpus::Int = 0)
+    return CT2mapOpts(
+        o.MatrixSize..., o.nTE, o.nT2, o.nRefAngles, o.nRefAnglesMin, REG_CODES[o.Reg], o.legacy, alpha_provided,
+        ngpus, 0, o.TE, o.T2Range..., o.T1, o.Threshold, o.MinRefAngle, o.RefConAngle,
+        nan_if_nothing(o.Chi2Factor), nan_if_nothing(o.NoiseLevel), nan_if_nothing(o.SetFlipAngle),
+    )
+end
+
+function CT2partOpts(o::T2partOptions{Float64})
+    return CT2partOpts(o.MatrixSize..., o.nT2, o.T2Range..., o.SPWin..., o.MPWin..., nan_if_nothing(o.Sigmoid))
+end
+
+function check_status(status::Cint)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:decaes_last_error, libdecaes_cuda), Cstring, ()))
+    return error("libdecaes_cuda failed with status $status: $msg")
+end
+
+"""
+    t2map_gpu!(maps, dist, image, opts; ngpus = 0)
+
+Drop-in body for the worker loop of `DECAES.T2mapSEcorr!` (src/T2mapSEcorr.jl:177-193).
+"""
+function t2map_gpu!(maps::T2Maps{Float64}, dist::T2Distributions{Float64}, image::Array{Float64, 4}, opts::T2mapOptions{Float64}; ngpus::Int = 0)
+    @assert size(image) == (opts.MatrixSize..., opts.nTE)
+    copts = Ref(CT2mapOpts(opts; alpha_provided = is_B1map_provided(maps), ngpus))
+    decaybasis = opts.SetFlipAngle === nothing ? maps.decaybasis : nothing # shared basis is not per-voxel (:581-587)
+    GC.@preserve image maps dist begin
+        out = Ref(CT2mapOut(
+            pointer(maps.gdn), pointer(maps.ggm), pointer(maps.gva), pointer(maps.fnr), pointer(maps.snr), pointer(maps.alpha),
+            pointer(dist.distributions),
+            ptr_or_null(maps.resnorm), ptr_or_null(maps.decaycurve), ptr_or_null(maps.mu), ptr_or_null(maps.chi2factor),
+            ptr_or_null(decaybasis),
+            Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL),
+        ))
+        status = ccall((:decaes_t2map, libdecaes_cuda), Cint,
+            (Ptr{Float64}, Ref{CT2mapOpts}, Ptr{Cvoid}, Ref{CT2mapOut}),
+            image, copts, C_NULL, out)
+        check_status(status)
+    end
+    return convert(Dict{String, Any}, maps), convert(Array{Float64, 4}, dist)
+end
+
+"""
+    t2part_gpu(T2distributions, opts)
+
+Drop-in body for the worker loop of `DECAES.T2partSEcorr` (src/T2partSEcorr.jl:58-68).
+"""
+function t2part_gpu(T2distributions::Array{Float64, 4}, opts::T2partOptions{Float64})
+    @assert size(T2distributions) == (opts.MatrixSize..., opts.nT2)
+    maps = T2Parts(opts)
+    copts = Ref(CT2partOpts(opts))
+    GC.@preserve T2distributions maps begin
+        status = ccall((:decaes_t2part, libdecaes_cuda), Cint,
+            (Ptr{Float64}, Ref{CT2partOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            T2distributions, copts, maps.sfr, maps.sgm, maps.mfr, maps.mgm)
+        check_status(status)
+    end
+    return convert(Dict{String, Any}, maps)
+end
+
+# Route the public Float64 entry points through the GPU library (the two-line patch a maintainer
+# would apply inside DECAES itself is shown in INTEGRATION.md).
+DECAES.T2mapSEcorr!(maps::T2Maps{Float64}, dist::T2Distributions{Float64}, image::Array{Float64, 4}, opts::T2mapOptions{Float64}) =
+    opts.legacy ? invoke(DECAES.T2mapSEcorr!, Tuple{T2Maps, T2Distributions, Array{T, 4}, T2mapOptions{T}} where {T}, maps, dist, image, opts) :
+    t2map_gpu!(maps, dist, image, opts)
+
+DECAES.T2partSEcorr(T2distributions::Array{Float64, 4}, opts::T2partOptions{Float64}) = t2part_gpu(T2distributions, opts)
+
+end # module

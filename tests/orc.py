@@ -15,9 +15,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liborc.so")
 
-_spec = importlib.util.spec_from_file_location("_decaes_abi", os.path.join(ROOT, "decaes.jl_b200", "_abi.py"))
-abi = importlib.util.module_from_spec(_spec)
-_spec.loader.exec_module(abi)
+def _load_package():
+    """The package directory `decaes.jl_b200/` has a dot in its name; import it as `decaes_jl_b200`
+    (same module name as tests/conftest.py and __graft_entry__.py so the ctypes classes are shared)."""
+    name = "decaes_jl_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    pkg_dir = os.path.join(ROOT, "decaes.jl_b200")
+    spec = importlib.util.spec_from_file_location(name, os.path.join(pkg_dir, "__init__.py"),
+                                                  submodule_search_locations=[pkg_dir])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+abi = _load_package()._abi  # struct definitions only; importing the package does not load the CUDA library
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)

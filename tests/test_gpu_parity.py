@@ -1,0 +1,201 @@
+"""GPU parity tests: libdecaes_cuda (through its C ABI, host-pointer entry points) against the CPU
+oracle on identical seeded inputs.  Tolerances are the north_star ones (tests/parity.py):
+distributions rel 1e-6 / abs 1e-9, flip angle / MWF / gmT2 abs 1e-6; voxels whose active set
+differs are counted.  Each config asserts a bound on the fraction of voxels outside tolerance."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+# (name, nTE, TE, nT2, Reg, extra opts, part windows, nvox, max fraction out of tolerance)
+CONFIGS = [
+    ("cfg1_none", 32, 10e-3, 40, "none", {}, {}, 4096, 0.01),
+    ("cfg2_lcurve48", 48, 8e-3, 40, "lcurve", {}, {}, 1024, 0.02),
+    ("cfg3_lcurve56", 56, 7e-3, 40, "lcurve", {}, {}, 1024, 0.02),
+    ("cfg4_chi2", 48, 8e-3, 60, "chi2", {"Chi2Factor": 1.02}, {}, 1024, 0.02),
+    ("cfg4_gcv", 48, 8e-3, 60, "gcv", {}, {}, 256, 0.03),
+    ("cfg5_mdp", 32, 10e-3, 60, "mdp", {"NoiseLevel": 1e-3}, {"SPWin": (10e-3, 200e-3), "MPWin": (200e-3, 2.0)}, 1024,
+     0.02),
+]
+
+
+def gpu_t2map(pkg, orc, img, o, p, **alloc_kw):
+    nvox, nTE = img.shape
+    arrs, out = orc.alloc_outputs(nvox, nTE, o.nT2, part=p is not None, **alloc_kw)
+    L = pkg.lib()
+    rc = L.decaes_t2map(img.ctypes.data, C.byref(o), C.byref(p) if p is not None else None, C.byref(out))
+    assert rc == 0, L.decaes_last_error().decode()
+    arrs["dist"] = arrs["dist"].reshape(o.nT2, nvox).T
+    if "decaycurve" in arrs:
+        arrs["decaycurve"] = arrs["decaycurve"].reshape(nTE, nvox).T
+    return arrs
+
+
+@pytest.mark.parametrize("name,nTE,TE,nT2,Reg,extra,part_kw,nvox,maxfrac", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_gpu_matches_oracle(pkg, orc, name, nTE, TE, nT2, Reg, extra, part_kw, nvox, maxfrac):
+    img = orc.mock_image(nvox, nTE, TE, seed=CONFIGS.index(next(c for c in CONFIGS if c[0] == name)) + 1)
+    o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, TE, Reg=Reg, ngpus=1, **extra)
+    p = orc.make_t2part_opts((nvox, 1, 1), nT2, **part_kw)
+    ref, st = orc.t2map(img, o, p)
+    got = gpu_t2map(pkg, orc, img, o, p)
+    rep = parity.compare(ref, got)
+    print(name, rep, "oracle early returns:", st.early_returns)
+    assert rep["nan_mismatch"] == 0
+    assert rep["frac_out_of_tolerance"] <= maxfrac, rep
+    # voxels with the same active set must agree far better than the tolerance
+    assert rep["dist_fail_same_support"] <= max(2, int(0.005 * nvox)), rep
+    stats = pkg.last_stats()
+    assert stats["voxels_processed"] == nvox and stats["kernel_launches"] >= 2
+
+
+def test_optional_outputs_and_threshold(pkg, orc):
+    nvox, nTE, nT2, TE = 512, 32, 40, 10e-3
+    img = orc.mock_image(nvox, nTE, TE, seed=11)
+    img[::5, 0] = 0.0  # below threshold -> skipped
+    o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, TE, Reg="lcurve", ngpus=1)
+    p = orc.make_t2part_opts((nvox, 1, 1), nT2)
+    kw = dict(save_curve=True, save_basis=True)
+    ref, st = orc.t2map(img, o, p, **kw)
+    got = gpu_t2map(pkg, orc, img, o, p, **kw)
+    skipped = np.zeros(nvox, bool)
+    skipped[::5] = True
+    for k in orc.MAP_NAMES + orc.PART_NAMES + ["mu", "chi2factor", "resnorm"]:
+        assert np.all(np.isnan(got[k][skipped])), k
+        assert np.all(np.isfinite(got[k][~skipped])), k
+    assert np.all(np.isnan(got["dist"][skipped]))
+    rep = parity.compare(ref, got)
+    assert rep["frac_out_of_tolerance"] <= 0.02, rep
+    same = ~(((ref["dist"] > 0) != (got["dist"] > 0)).any(1)) & ~skipped
+    np.testing.assert_allclose(got["decaycurve"][same], ref["decaycurve"][same], rtol=1e-6, atol=1e-9)
+    gb = got["decaybasis"].reshape(nT2, nTE, nvox)[:, :, same]
+    rb = ref["decaybasis"].reshape(nT2, nTE, nvox)[:, :, same]
+    np.testing.assert_allclose(gb, rb, rtol=1e-6, atol=1e-12)
+    assert pkg.last_stats()["voxels_processed"] == int((~skipped).sum())
+
+
+def test_set_flip_angle_and_b1_map(pkg, orc):
+    nvox, nTE, nT2, TE = 256, 32, 40, 10e-3
+    img = orc.mock_image(nvox, nTE, TE, seed=12)
+    o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, TE, Reg="none", SetFlipAngle=170.0, ngpus=1)
+    ref, _ = orc.t2map(img, o)
+    got = gpu_t2map(pkg, orc, img, o, None)
+    assert np.all(got["alpha"] == 170.0)
+    assert parity.compare(ref, got)["frac_out_of_tolerance"] <= 0.01
+    b1 = np.linspace(130.0, 179.0, nvox)
+    o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, TE, Reg="chi2", Chi2Factor=1.02, alpha_provided=True, ngpus=1)
+    ref, _ = orc.t2map(img, o, alpha_init=b1)
+    got = gpu_t2map(pkg, orc, img, o, None, alpha_init=b1)
+    np.testing.assert_array_equal(got["alpha"], b1)
+    assert parity.compare(ref, got)["frac_out_of_tolerance"] <= 0.02
+
+
+@pytest.mark.parametrize("nTE,nT2", [(4, 2), (5, 3), (8, 8), (47, 47), (64, 60)])
+def test_odd_sizes(pkg, orc, nTE, nT2):
+    nvox = 64
+    img = orc.mock_image(nvox, nTE, 10e-3, seed=nTE)
+    for Reg, extra in [("none", {}), ("lcurve", {}), ("chi2", {"Chi2Factor": 1.05}), ("mdp", {"NoiseLevel": 1e-2})]:
+        o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, 10e-3, Reg=Reg, ngpus=1, **extra)
+        ref, _ = orc.t2map(img, o)
+        got = gpu_t2map(pkg, orc, img, o, None)
+        rep = parity.compare(ref, got)
+        assert rep["nan_mismatch"] == 0
+        assert rep["frac_out_of_tolerance"] <= 0.1, (Reg, rep)
+
+
+def test_t2part_standalone_bit_exact_structure(pkg, orc):
+    nvox, nT2 = 4096, 40
+    rng = np.random.default_rng(0)
+    dist = np.asfortranarray(rng.random((nvox, nT2)) * (rng.random((nvox, nT2)) < 0.2))
+    dist[7] = 0.0          # all-zero voxel: nothing written
+    dist[9, 3] = np.nan    # NaN voxel: skipped
+    for Sigmoid in (None, 5e-3):
+        p = orc.make_t2part_opts((nvox, 1, 1), nT2, Sigmoid=Sigmoid)
+        ref = orc.t2part(dist, p)
+        outs = {k: np.full(nvox, np.nan) for k in orc.PART_NAMES}
+        rc = pkg.lib().decaes_t2part(dist.ctypes.data, C.byref(p), *[outs[k].ctypes.data for k in orc.PART_NAMES])
+        assert rc == 0
+        for k in orc.PART_NAMES:
+            assert np.array_equal(np.isnan(ref[k]), np.isnan(outs[k])), k
+            np.testing.assert_allclose(outs[k], ref[k], rtol=1e-13, equal_nan=True)
+
+
+def test_setup_tables_match_oracle(pkg, orc):
+    o = orc.make_t2map_opts((1, 1, 1), 48, 40, 10e-3)
+    et, t2, ang, basis, _ = orc.setup_tables(o)
+    g_et, g_t2, g_ang = np.empty(48), np.empty(40), np.empty(64)
+    g_basis = np.empty(64 * 40 * 48)
+    rc = pkg.lib().decaes_setup_tables(C.byref(o), g_et.ctypes.data, g_t2.ctypes.data, g_ang.ctypes.data,
+                                       g_basis.ctypes.data)
+    assert rc == 0
+    np.testing.assert_array_equal(g_et, et)
+    np.testing.assert_array_equal(g_t2, t2)
+    np.testing.assert_array_equal(g_ang, ang)
+    gb = g_basis.reshape(64, 40, 48).transpose(2, 1, 0)
+    np.testing.assert_allclose(gb, basis, rtol=1e-13, atol=1e-16)
+    # docstring known answers straight from the GPU tables (src/T2mapSEcorr.jl:134)
+    assert abs(gb[0, 0, 0] - 0.0277684) < 5e-8 and abs(gb[0, 1, 0] - 0.0315296) < 5e-8
+
+
+def test_python_api_drop_in(pkg, orc):
+    """T2mapSEcorr / T2partSEcorr with the reference's keyword API (docstring example shape)."""
+    nTE, TE = 48, 10e-3
+    img = orc.mock_image(6 * 5 * 2, nTE, TE, seed=3).reshape(6, 5, 2, nTE, order="F")
+    maps, dist = pkg.T2mapSEcorr(img, TE=TE, nT2=40, T2Range=(10e-3, 2.0), Reg="lcurve", Silent=True,
+                                 SaveRegParam=True, ngpus=1)
+    assert set(["echotimes", "t2times", "refangleset", "decaybasisset", "gdn", "ggm", "gva", "fnr", "snr", "alpha",
+                "mu", "chi2factor"]) <= set(maps)
+    assert dist.shape == (6, 5, 2, 40) and maps["decaybasisset"].shape == (48, 40, 64)
+    np.testing.assert_allclose(maps["t2times"][:5], [0.01, 0.0114551, 0.013122, 0.0150315, 0.0172188], rtol=5e-6)
+    part = pkg.T2partSEcorr(dist, T2Range=(10e-3, 2.0), SPWin=(10e-3, 25e-3), MPWin=(25e-3, 200e-3), Silent=True)
+    assert set(part) == {"sfr", "sgm", "mfr", "mgm"} and part["sfr"].shape == (6, 5, 2)
+    # same numbers through the oracle
+    o = orc.make_t2map_opts((60, 1, 1), nTE, 40, TE, Reg="lcurve")
+    p = orc.make_t2part_opts((60, 1, 1), 40)
+    ref, _ = orc.t2map(img.reshape(60, nTE, order="F"), o, p)
+    got = {"dist": dist.reshape(60, 40, order="F"), "alpha": maps["alpha"].ravel(order="F"),
+           "ggm": maps["ggm"].ravel(order="F"), "sfr": part["sfr"].ravel(order="F")}
+    assert parity.compare(ref, got)["voxels_out_of_tolerance"] <= 2
+
+
+def test_full_size_properties(pkg, orc):
+    """Size-independent properties on a larger slab generated on the device (no oracle):
+    gdn == sum(dist); fused T2part == standalone T2part; scaling the image scales the
+    distribution and leaves alpha / ggm / sfr unchanged (linearity of the normalised pipeline)."""
+    import torch
+    nvox, nTE, nT2, TE = 120_000, 56, 40, 7e-3
+    dev = torch.device("cuda:0")
+    img = torch.empty((nTE, nvox), dtype=torch.float64, device=dev)
+    pkg.mock_image_device(img.data_ptr(), nvox, nvox, 0, nTE, TE, seed=3)
+    o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, TE, Reg="lcurve", ngpus=1)
+    p = orc.make_t2part_opts((nvox, 1, 1), nT2)
+
+    def run(image):
+        names = ["gdn", "ggm", "gva", "fnr", "snr", "alpha", "sfr", "sgm", "mfr", "mgm"]
+        t = {k: torch.full((nvox,), float("nan"), dtype=torch.float64, device=dev) for k in names}
+        t["dist"] = torch.full((nT2, nvox), float("nan"), dtype=torch.float64, device=dev)
+        out = pkg.make_out({k: v.data_ptr() for k, v in t.items()})
+        pkg.t2map_device(image.data_ptr(), nvox, nvox, o, p, out, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return t
+    a = run(img)
+    assert pkg.last_stats()["voxels_processed"] == nvox
+    assert torch.isfinite(a["dist"]).all() and (a["dist"] >= 0).all()
+    torch.testing.assert_close(a["gdn"], a["dist"].sum(0), rtol=1e-12, atol=0)
+    s = [torch.full((nvox,), float("nan"), dtype=torch.float64, device=dev) for _ in range(4)]
+    pkg.t2part_device(a["dist"].data_ptr(), nvox, nvox, p, *[x.data_ptr() for x in s],
+                      torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for k, x in zip(["sfr", "sgm", "mfr", "mgm"], s):
+        torch.testing.assert_close(x, a[k], rtol=1e-13, atol=0, equal_nan=True)
+    b = run(img * 8.0)  # power of two: exact scaling of the normalised problem
+    torch.testing.assert_close(b["dist"], a["dist"] * 8.0, rtol=0, atol=0)
+    for k in ("alpha", "ggm", "sfr", "gva"):
+        torch.testing.assert_close(b[k], a[k], rtol=0, atol=0, equal_nan=True)
+    # checksum of checksums against a second identical run: the pipeline is deterministic
+    c = run(img)
+    assert torch.equal(c["dist"], a["dist"])
