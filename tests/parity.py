@@ -46,4 +46,24 @@ def compare(ref, got, scalars=("alpha", "sfr", "ggm"), extra=("gdn", "gva", "fnr
             rep[k + "_median_rel"] = float(np.nanmedian(r)) if nvox else 0.0
     rep["voxels_out_of_tolerance"] = int(fails.sum())
     rep["frac_out_of_tolerance"] = float(fails.mean()) if nvox else 0.0
+    # Regularisation-parameter "path flips": the L-curve / GCV / Brent searches take discrete decisions on
+    # quantities that are noisy at the 1e-13 level, so two faithful implementations (or the oracle
+    # itself under a 1-ulp input perturbation, tests/test_oracle_sensitivity.py) pick a slightly
+    # different mu for a few percent of voxels.  Those voxels are counted and reported separately.
+    if "mu" in ref and "mu" in got:
+        m0, m1 = np.asarray(ref["mu"], dtype=float), np.asarray(got["mu"], dtype=float)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            dlog = np.abs(np.log(m0) - np.log(m1))
+        same = (m0 == m1) | (np.isnan(m0) & np.isnan(m1)) | (dlog <= 1e-9)
+        flip = ~same
+        rep["mu_flips"] = int(flip.sum())
+        rep["mu_flip_frac"] = float(flip.mean()) if nvox else 0.0
+        rep["mu_flip_median_dlog"] = float(np.nanmedian(dlog[flip])) if flip.any() else 0.0
+        rep["mu_flip_max_dlog"] = float(np.nanmax(dlog[flip])) if flip.any() else 0.0
+        rep["out_of_tolerance_same_mu"] = int((fails & ~flip).sum())
+        rep["frac_out_of_tolerance_same_mu"] = float((fails & ~flip).mean()) if nvox else 0.0
+    else:
+        rep["mu_flips"], rep["mu_flip_frac"] = 0, 0.0
+        rep["out_of_tolerance_same_mu"] = rep["voxels_out_of_tolerance"]
+        rep["frac_out_of_tolerance_same_mu"] = rep["frac_out_of_tolerance"]
     return rep
