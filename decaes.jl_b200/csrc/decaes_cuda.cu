@@ -115,10 +115,28 @@ __global__ void basis_setup_kernel(const __grid_constant__ SetupParams S) {
   }
 }
 
+// G_k = A_k' A_k for every grid angle (Gram solver): one thread per (k, p, q)
+__global__ void gram_setup_kernel(const __grid_constant__ SetupParams S, double *gram_set, int ldg) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = S.nT2;
+  if (t >= (long long)S.nA * n * n) return;
+  int k = (int)(t / (n * n)), p = (int)((t / n) % n), q = (int)(t % n);
+  const double *rm = S.basis_rm + (size_t)k * S.copy_elems;
+  double a0 = 0.0, a1 = 0.0;
+  int i = 0;
+  for (; i + 1 < S.nTE; i += 2) {
+    a0 = fma(rm[i * S.ld + p], rm[i * S.ld + q], a0);
+    a1 = fma(rm[(i + 1) * S.ld + p], rm[(i + 1) * S.ld + q], a1);
+  }
+  if (i < S.nTE) a0 = fma(rm[i * S.ld + p], rm[i * S.ld + q], a0);
+  gram_set[(size_t)k * n * ldg + p * ldg + q] = a0 + a1;
+}
+
+template <bool GRAM>
 __global__ void __launch_bounds__(32) voxel_pipeline_kernel(const __grid_constant__ PipeParams P) {
   extern __shared__ __align__(128) double smem[];
   double *gscratch = P.scratch + (size_t)blockIdx.x * P.scratch_per_warp;
-  Warp W(P, smem, gscratch);
+  Warp<GRAM> W(P, smem, gscratch);
   const int lane = lane_id();
   if (lane == 0) {
     mbar_init(W.bar, 1);
@@ -413,9 +431,9 @@ static int make_part_tables(const decaes_t2part_opts *o, PartTables *t) {
 
 // ---- per-device workspace (grow-only, cached across calls) ----
 struct DeviceWs {
-  double *basis_rm = nullptr, *basis_cm = nullptr, *dbasis_cm = nullptr, *scratch = nullptr;
+  double *basis_rm = nullptr, *basis_cm = nullptr, *dbasis_cm = nullptr, *scratch = nullptr, *gram_set = nullptr;
   unsigned long long *counters = nullptr;
-  size_t basis_rm_cap = 0, basis_cm_cap = 0, scratch_cap = 0;
+  size_t basis_rm_cap = 0, basis_cm_cap = 0, scratch_cap = 0, gram_cap = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_pending = false;
   int sm_count = 0;
@@ -454,6 +472,11 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.epg_kmax = nTE / 2 + 3;
   int epg_elems = 3 * P.epg_kmax * 32;
   P.a_elems = std::max(std::max(P.rows_alloc * P.ld, P.copy_elems), epg_elems);
+  // solver variant: normal-equation active set (default) or the QR port (DECAES_SOLVER=qr, kept for A/B checks)
+  const char *sv = getenv("DECAES_SOLVER");
+  P.gram = !(sv && strcmp(sv, "qr") == 0);
+  P.ldg = nT2 | 1;
+  if (P.gram) P.a_elems = nT2 * P.ldg;
   P.a_elems = (P.a_elems + 1) & ~1;
   P.fixed_alpha = fixed, P.alpha_provided = o->alpha_provided;
   P.maxeval = o->nRefAngles;
@@ -482,16 +505,21 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     memcpy(P.weights, pt.weights, sizeof pt.weights);
   }
 
-  SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems);
+  SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems, P.gram);
   plan->smem_bytes = L.total_bytes;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
   if ((size_t)plan->smem_bytes > prop.sharedMemPerBlockOptin)
     return fail(DECAES_EUNSUPPORTED, "problem needs %d bytes of shared memory per warp (> %zu)", plan->smem_bytes,
                 prop.sharedMemPerBlockOptin);
-  CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, voxel_pipeline_kernel, 32, plan->smem_bytes));
+  if (P.gram) {
+    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, voxel_pipeline_kernel<true>, 32, plan->smem_bytes));
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, voxel_pipeline_kernel<false>, 32, plan->smem_bytes));
+  }
   if (occ < 1) return fail(DECAES_ECUDA, "voxel_pipeline_kernel cannot be resident (occupancy 0)");
   plan->grid = occ * prop.multiProcessorCount;
 
@@ -512,6 +540,8 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     ws.basis_cm_cap = cm;
   }
   if ((rc = ensure(&ws.scratch, &ws.scratch_cap, (size_t)plan->grid * sl.total))) return rc;
+  if ((rc = ensure(&ws.gram_set, &ws.gram_cap, (size_t)nA * nT2 * P.ldg))) return rc;
+  P.gram_set = ws.gram_set;
   if (!ws.counters) CUDA_TRY(cudaMalloc(&ws.counters, 8 * sizeof(unsigned long long)));
   for (int i = 0; i < 4; i++)
     if (!ws.ev[i]) CUDA_TRY(cudaEventCreate(&ws.ev[i]));
@@ -549,10 +579,18 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
   int nt = plan.S.nA * plan.S.nT2;
   basis_setup_kernel<<<(nt + 63) / 64, 64, 0, stream>>>(plan.S);
   CUDA_TRY(cudaGetLastError());
+  if (P.gram) {
+    long long ng = (long long)plan.S.nA * plan.S.nT2 * plan.S.nT2;
+    gram_setup_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, stream>>>(plan.S, ws.gram_set, P.ldg);
+    CUDA_TRY(cudaGetLastError());
+  }
   CUDA_TRY(cudaEventRecord(ws.ev[1], stream));
   int64_t ngroups = (nvox + DECAES_GROUP - 1) / DECAES_GROUP;
   int grid = (int)std::min<int64_t>(plan.grid, std::max<int64_t>(ngroups, 1));
-  voxel_pipeline_kernel<<<grid, 32, plan.smem_bytes, stream>>>(P);
+  if (P.gram)
+    voxel_pipeline_kernel<true><<<grid, 32, plan.smem_bytes, stream>>>(P);
+  else
+    voxel_pipeline_kernel<false><<<grid, 32, plan.smem_bytes, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(ws.ev[2], stream));
   ws.ev_pending = true;
@@ -571,7 +609,7 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
   st->setup_ms = std::max(st->setup_ms, (double)a);
   st->pipeline_ms = std::max(st->pipeline_ms, (double)b);
   st->voxels_processed += (int64_t)c[1];
-  st->kernel_launches += 2;
+  st->kernel_launches += 3;
   ws.ev_pending = false;
   return DECAES_OK;
 }

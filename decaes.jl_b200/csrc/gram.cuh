@@ -1,0 +1,301 @@
+// Warp-cooperative Lawson–Hanson NNLS on the normal equations ("Gram form"), one voxel per warp.
+//
+// Same active-set algorithm as the reference (src/NNLS.jl:605-1061 through the warm-started
+// drivers src/lsqnonneg.jl:30-164): identical pivot rule (largest positive dual, first on ties),
+// identical accept/reject test on the sign of the entering coefficient (b1/A1 > 0, src/NNLS.jl:300),
+// identical feasibility step / removal rule and 3n iteration cap.  What changes is the linear
+// algebra underneath: instead of reflecting the whole nTE x nT2 matrix for every pivot (a BLAS-2
+// sweep over ~18 KB of shared memory per pivot), the warp keeps
+//     G = A'A (+ mu^2 I)   n x n, shared memory (per voxel) or L2 (per flip-angle grid point)
+//     c = A'b              n
+//     M = L^-1             inverse Cholesky factor of G_PP in pivot order, packed lower triangle
+// so that appending a column is two O(k) fma chains per lane plus two warp reductions, the
+// solution is s = M'(M c_P) maintained incrementally, and the dual is w = c - G_P x_P.
+// The minimiser of the Tikhonov problems (mu > 0) is unique, so those solves may be warm-started
+// from the active set of the nearest mu already solved; unregularised solves follow the
+// reference's cold-start path pivot by pivot and are polished with one step of iterative
+// refinement on the explicit residual (done by the caller, which owns A).
+#pragma once
+#include "common.cuh"
+
+namespace decaes {
+
+struct GramProb {
+  const double *G;  // n x n symmetric, row-major, leading dimension ldg (shared or global memory)
+  int ldg;
+  const double *c;  // [n] shared memory
+  double mu2;       // mu^2 (0 for the plain problem)
+  int n;
+  int max_set;      // min(m, n) for the plain problem, n for Tikhonov (src/NNLS.jl:627, :851)
+};
+
+struct GramWs {  // shared-memory scratch of one warp
+  double *M;     // packed lower triangle [n(n+1)/2]: M[t][u] at t(t+1)/2 + u
+  double *y;     // [n] y = M c_P
+  double *s;     // [n] s = M' y   (solution on P, in pivot order)
+  double *x;     // [n] current feasible solution, indexed by column
+  double *w;     // [n] dual, indexed by column
+  double *t1;    // [n] scratch
+  double *t2;    // [n] scratch
+  int *P;        // [n] active columns in pivot order
+};
+
+struct GramOut {
+  int k;                     // number of active columns
+  unsigned long long mask;   // active set as a bit mask
+  double xnorm_sq;           // sum of squares of the solution
+};
+
+#define GM(t, u) M[((t) * ((t) + 1)) / 2 + (u)]
+
+// Append column j to the factorisation (pivot position k).  Returns false (and changes nothing)
+// when the column is numerically dependent (d^2 <= 0) or, with `need_positive`, when its
+// coefficient would not be positive (the reference's b1/A1 > 0 test).
+__device__ __noinline__ bool gram_append(const GramProb &p, const GramWs &ws, int &k, int j, bool need_positive) {
+  const int lane = lane_id();
+  double *M = ws.M;
+  // g_t = G[P[t]][j]
+  for (int t = lane; t < k; t += 32) ws.t1[t] = p.G[ws.P[t] * p.ldg + j];
+  __syncwarp();
+  // l = M g  (lane <-> row t)
+  double ll = 0.0, ly = 0.0;
+  for (int t = lane; t < k; t += 32) {
+    const double *row = M + (t * (t + 1)) / 2;
+    double a0 = 0.0, a1 = 0.0;
+    int u = 0;
+    for (; u + 1 <= t; u += 2) {
+      a0 = fma(row[u], ws.t1[u], a0);
+      a1 = fma(row[u + 1], ws.t1[u + 1], a1);
+    }
+    if (u <= t) a0 = fma(row[u], ws.t1[u], a0);
+    double lt = a0 + a1;
+    ws.t2[t] = lt;
+    ll = fma(lt, lt, ll);
+    ly = fma(lt, ws.y[t], ly);
+  }
+  ll = warp_sum(ll), ly = warp_sum(ly);
+  const double d2 = (p.G[j * p.ldg + j] + p.mu2) - ll;
+  if (!(d2 > 0.0)) return false;
+  const double d = sqrt(d2), dinv = 1.0 / d;
+  const double ynew = (p.c[j] - ly) * dinv;
+  if (need_positive && !(ynew > 0.0)) return false;
+  __syncwarp();
+  // new row of M: m_u = -dinv * sum_{t >= u} l_t M[t][u]   (lane <-> column u)
+  double *newrow = M + (k * (k + 1)) / 2;
+  for (int u = lane; u < k; u += 32) {
+    double a0 = 0.0, a1 = 0.0;
+    int t = u;
+    for (; t + 1 < k; t += 2) {
+      a0 = fma(ws.t2[t], GM(t, u), a0);
+      a1 = fma(ws.t2[t + 1], GM(t + 1, u), a1);
+    }
+    if (t < k) a0 = fma(ws.t2[t], GM(t, u), a0);
+    double mu_ = -dinv * (a0 + a1);
+    newrow[u] = mu_;
+    ws.s[u] = fma(ynew, mu_, ws.s[u]);
+  }
+  if (lane == 0) {
+    newrow[k] = dinv;
+    ws.y[k] = ynew;
+    ws.s[k] = ynew * dinv;
+    ws.P[k] = j;
+  }
+  __syncwarp();
+  k += 1;
+  return true;
+}
+
+// Rebuild rows [from, k) of M (after a removal or for a warm start); P[0:k) already holds the columns.
+__device__ __noinline__ void gram_rebuild(const GramProb &p, const GramWs &ws, int &k, int from) {
+  const int lane = lane_id();
+  const int kold = k;
+  double *M = ws.M;
+  // s = M[0:from]' y[0:from]
+  for (int u = lane; u < kold; u += 32) {
+    double a = 0.0;
+    for (int t = u; t < from; t++) a = fma(GM(t, u), ws.y[t], a);
+    ws.s[u] = a;
+  }
+  __syncwarp();
+  k = from;
+  for (int t = from; t < kold; t++) {
+    int j = ws.P[t];
+    __syncwarp();
+    if (!gram_append(p, ws, k, j, false)) {
+      // numerically dependent column inside a set that was independent a moment ago: drop it
+      if (lane == 0) {
+        ws.x[j] = 0.0;
+      }
+      __syncwarp();
+    }
+    // gram_append wrote P[k-1] = j at the compacted position; later entries are still at t+1..
+  }
+}
+
+// w_j = c_j - sum_t G[P[t]][j] * xs_t  for every column (the entries of active columns are forced to 0).
+// xs = coefficients in pivot order (ws.s after a solve).
+__device__ __noinline__ void gram_dual(const GramProb &p, const GramWs &ws, int k, unsigned long long mask) {
+  const int lane = lane_id();
+  for (int j = lane; j < p.n; j += 32) {
+    double a0 = p.c[j], a1 = 0.0;
+    int t = 0;
+    for (; t + 1 < k; t += 2) {
+      a0 = fma(-p.G[ws.P[t] * p.ldg + j], ws.s[t], a0);
+      a1 = fma(-p.G[ws.P[t + 1] * p.ldg + j], ws.s[t + 1], a1);
+    }
+    if (t < k) a0 = fma(-p.G[ws.P[t] * p.ldg + j], ws.s[t], a0);
+    ws.w[j] = ((mask >> j) & 1ull) ? 0.0 : a0 + a1;
+  }
+  __syncwarp();
+}
+
+// Lawson–Hanson main loop.  cold: start from the empty set with the reference's warm dual
+// (src/lsqnonneg.jl:44-70).  warm: start from the feasible point ws.x supported on `mask`.
+__device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, bool warm, unsigned long long mask) {
+  const int lane = lane_id();
+  const int n = p.n;
+  int k = 0, iter = 0;
+  const int max_iter = 3 * n;
+  bool need_solve_check = false;
+
+  if (!warm) {
+    mask = 0ull;
+    // dual as if the last column were active; w[n-1] = 0, or 1 if every other dual is <= 0
+    const double xj = p.c[n - 1] / (p.G[(n - 1) * p.ldg + (n - 1)] + p.mu2);
+    bool anypos = false;
+    for (int j = lane; j < n; j += 32) {
+      double wj = (j < n - 1) ? fma(-p.G[(n - 1) * p.ldg + j], xj, p.c[j]) : 0.0;
+      ws.w[j] = wj;
+      ws.x[j] = 0.0;
+      anypos |= !(wj <= 0.0);
+    }
+    if (!__any_sync(DECAES_FULL_MASK, anypos) && lane == 0) ws.w[n - 1] = 1.0;
+    __syncwarp();
+  } else {
+    // factor the inherited set (ascending column order)
+    unsigned long long m2 = mask;
+    int kk = 0;
+    while (m2) {
+      int j = __ffsll((long long)m2) - 1;
+      m2 &= m2 - 1;
+      if (lane == 0) ws.P[kk] = j;
+      kk++;
+    }
+    for (int j = lane; j < n; j += 32)
+      if (!((mask >> j) & 1ull)) ws.x[j] = 0.0;
+    __syncwarp();
+    k = kk;
+    gram_rebuild(p, ws, k, 0);
+    if (k != kk) {  // a column was dropped as dependent: rebuild the mask
+      mask = 0ull;
+      for (int t = 0; t < k; t++) mask |= 1ull << ws.P[t];
+    }
+    need_solve_check = (k > 0);
+    if (k == 0) {
+      for (int j = lane; j < n; j += 32) ws.w[j] = p.c[j];
+      __syncwarp();
+    }
+  }
+
+  bool terminated = false;
+  while (true) {
+    if (!need_solve_check) {
+      if (k >= p.max_set) break;
+      // ---- entering column: largest positive dual, first on ties; test its coefficient ----
+      bool accepted = false;
+      while (true) {
+        double best = 0.0;
+        int bj = 0x7fffffff;
+        for (int j = lane; j < n; j += 32) {
+          double v = ws.w[j];
+          if (!((mask >> j) & 1ull) && v > best) best = v, bj = j;
+        }
+        warp_argmax_first(best, bj);
+        if (!(best > 0.0)) {
+          terminated = true;
+          break;
+        }
+        if (gram_append(p, ws, k, bj, true)) {
+          mask |= 1ull << bj;
+          accepted = true;
+          break;
+        }
+        if (lane == 0) ws.w[bj] = 0.0;  // rejected (src/NNLS.jl:652-657)
+        __syncwarp();
+      }
+      if (terminated || !accepted) break;
+    }
+    need_solve_check = false;
+
+    // ---- secondary loop: keep the iterate feasible (src/NNLS.jl:692-786) ----
+    while (true) {
+      iter += 1;
+      if (iter > max_iter) {
+        terminated = true;
+        break;
+      }
+      double al = 2.0;
+      int imv = 0x7fffffff;
+      for (int t = lane; t < k; t += 32) {
+        double st = ws.s[t];
+        if (st <= 0.0) {
+          double xi = ws.x[ws.P[t]];
+          double tt = -xi / (st - xi);
+          if (al > tt) al = tt, imv = t;
+        }
+      }
+      warp_argmin_first(al, imv);
+      if (!(al < 2.0)) break;  // all coefficients feasible
+      for (int t = lane; t < k; t += 32) {
+        int jx = ws.P[t];
+        ws.x[jx] = fma(al, ws.s[t] - ws.x[jx], ws.x[jx]);
+      }
+      __syncwarp();
+      // remove imv, then any other non-positive coefficient (first found), compacting P
+      int first_removed = imv;
+      while (true) {
+        if (lane == 0) {
+          int jr = ws.P[imv];
+          ws.x[jr] = 0.0;
+          for (int t = imv; t < k - 1; t++) ws.P[t] = ws.P[t + 1];
+        }
+        mask &= ~(1ull << ws.P[imv]);  // evaluated before lane 0's shift is visible? see below
+        __syncwarp();
+        k -= 1;
+        if (imv < first_removed) first_removed = imv;
+        unsigned bad0 = __ballot_sync(DECAES_FULL_MASK, lane < k && ws.x[ws.P[lane]] <= 0.0);
+        unsigned bad1 = __ballot_sync(DECAES_FULL_MASK, lane + 32 < k && ws.x[ws.P[lane + 32]] <= 0.0);
+        if (bad0) imv = __ffs(bad0) - 1;
+        else if (bad1) imv = 32 + __ffs(bad1) - 1;
+        else break;
+      }
+      // rebuild the mask from P (cheap, avoids ordering hazards) and the factor from the first hole
+      mask = 0ull;
+      for (int t = 0; t < k; t++) mask |= 1ull << ws.P[t];
+      int knew = k;
+      gram_rebuild(p, ws, knew, first_removed);
+      if (knew != k) {
+        k = knew;
+        mask = 0ull;
+        for (int t = 0; t < k; t++) mask |= 1ull << ws.P[t];
+      }
+    }
+    if (terminated) break;
+
+    for (int t = lane; t < k; t += 32) ws.x[ws.P[t]] = ws.s[t];
+    __syncwarp();
+    gram_dual(p, ws, k, mask);
+  }
+
+  GramOut o;
+  o.k = k;
+  o.mask = mask;
+  double acc = 0.0;
+  for (int j = lane; j < n; j += 32) acc = fma(ws.x[j], ws.x[j], acc);
+  o.xnorm_sq = warp_sum(acc);
+  return o;
+}
+
+#undef GM
+
+}  // namespace decaes

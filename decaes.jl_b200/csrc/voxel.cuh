@@ -7,6 +7,7 @@
 // 1-D optimisers src/optimization.jl:71-128, 191-219, 319-413.
 #pragma once
 #include "nnls.cuh"
+#include "gram.cuh"
 
 namespace decaes {
 
@@ -33,6 +34,8 @@ struct PipeParams {
   const double *basis_rm;   // [nA][copy_elems]  row-major, leading dimension ld (TMA source)
   const double *basis_cm;   // [nA][nT2][nTE]
   const double *dbasis_cm;  // [nA][nT2][nTE]   d/d(alpha in degrees)
+  const double *gram_set;   // [nA][nT2*ldg]     A_k'A_k per grid angle (Gram solver)
+  int gram, ldg;            // solver variant (1 = normal-equation active set), leading dimension of G
   double angles[DECAES_MAX_ANGLES];                            // flip-angle grid (degrees)
   double logT2[DECAES_MAX_NT2], E2[DECAES_MAX_NT2];            // log(T2_j), exp(-(TE/2)/T2_j)
   double weights[DECAES_MAX_NT2];                              // sigmoid weights (has_sigmoid)
@@ -44,10 +47,11 @@ struct PipeParams {
 
 // layout of the per-warp global scratch (in doubles)
 struct ScratchLayout {
-  int pristine, slots_x, lc_pts, lc_states, fa_u, fa_du, gcv_gamma, gcv_mat, total;
+  int pristine, pristine_cm, slots_x, lc_pts, lc_states, fa_u, fa_du, gcv_gamma, gcv_mat, total;
   __host__ __device__ ScratchLayout(int nTE, int nT2, int copy_elems, bool gcv) {
     int o = 0;
     pristine = o, o += copy_elems;
+    pristine_cm = o, o += nTE * nT2 + (nTE * nT2 & 1);
     slots_x = o, o += DECAES_NCACHE * nT2;
     lc_pts = o, o += DECAES_LC_MAX * 4;
     lc_states = o, o += DECAES_LC_MAX * 6;
@@ -61,12 +65,23 @@ struct ScratchLayout {
 
 // per-warp shared memory layout (in doubles, then ints)
 struct SmemLayout {
-  int A, b, u, x, w, bd, sig, fit, slot_mu, slot_r2, slot_x2, idx, bar, total_bytes;
-  __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems) {
+  int A, b, u, x, w, bd, sig, fit, slot_mu, slot_r2, slot_x2, slot_mask, idx, bar, total_bytes;
+  int M, c, y, s, t1, t2;  // Gram solver only
+  __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems, int gram) {
     int o = 0;
-    A = o, o += a_elems;
-    b = o, o += rows_alloc;
-    u = o, o += rows_alloc;
+    A = o, o += a_elems;  // QR: working matrix / EPG scratch.  Gram: G (nT2 x ldg)
+    b = u = M = c = y = s = t1 = t2 = 0;
+    if (gram) {
+      M = o, o += (nT2 * (nT2 + 1)) / 2;
+      c = o, o += nT2;
+      y = o, o += nT2;
+      s = o, o += nT2;
+      t1 = o, o += nT2;
+      t2 = o, o += nT2;
+    } else {
+      b = o, o += rows_alloc;
+      u = o, o += rows_alloc;
+    }
     x = o, o += nT2;
     w = o, o += nT2;
     bd = o, o += nTE;
@@ -75,15 +90,28 @@ struct SmemLayout {
     slot_mu = o, o += DECAES_NCACHE;
     slot_r2 = o, o += DECAES_NCACHE;
     slot_x2 = o, o += DECAES_NCACHE;
+    slot_mask = o, o += DECAES_NCACHE;
     bar = o, o += 2;
     idx = o, o += (nT2 + 1) / 2;
     total_bytes = ((o * 8) + 15) & ~15;
   }
 };
 
+struct Src {               // where the current basis of the Gram solver lives
+  const double *G;         // n x n Gram matrix (shared or global)
+  int ldg;
+  const double *Arm;       // row-major nTE x ld
+  const double *Acm;       // column-major [col * nTE + i]
+};
+
+template <bool GRAM>
 struct Warp {
+  Src cursrc;
   const PipeParams &P;
   NnlsWs ws;
+  GramWs gws;                    // Gram solver scratch
+  double *Gs, *cvec;             // per-voxel G = A'A and c = A'b in shared memory (Gram solver)
+  unsigned long long *slot_mask; // active set of each cache slot
   double *bd, *sig, *fit, *slot_mu, *slot_r2, *slot_x2;
   uint64_t *bar;
   unsigned phase;
@@ -96,10 +124,14 @@ struct Warp {
 
   __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
       : P(p), sl(p.nTE, p.nT2, p.copy_elems, p.reg == 2) {
-    SmemLayout L(p.nTE, p.nT2, p.rows_alloc, p.a_elems);
+    SmemLayout L(p.nTE, p.nT2, p.rows_alloc, p.a_elems, p.gram);
     ws.A = smem + L.A, ws.b = smem + L.b, ws.u = smem + L.u, ws.x = smem + L.x, ws.w = smem + L.w;
     ws.idx = (int *)(smem + L.idx);
     ws.ld = p.ld, ws.n = p.nT2, ws.m0 = p.nTE;
+    Gs = smem + L.A, cvec = smem + L.c;
+    gws.M = smem + L.M, gws.y = smem + L.y, gws.s = smem + L.s, gws.x = smem + L.x, gws.w = smem + L.w;
+    gws.t1 = smem + L.t1, gws.t2 = smem + L.t2, gws.P = (int *)(smem + L.idx);
+    slot_mask = (unsigned long long *)(smem + L.slot_mask);
     bd = smem + L.bd, sig = smem + L.sig, fit = smem + L.fit;
     slot_mu = smem + L.slot_mu, slot_r2 = smem + L.slot_r2, slot_x2 = smem + L.slot_x2;
     bar = (uint64_t *)(smem + L.bar);
@@ -214,9 +246,22 @@ struct Warp {
     xs = warp_bcast(bestx, 0), us = warp_bcast(bestu, 0);
   }
 
+  // EPG basis at `alpha` for this voxel (+ Gram matrix and right-hand side for the Gram solver)
+  __device__ void basis_at(double alpha, long long v) {
+    if constexpr (GRAM) {
+      if (P.nTE <= 63) epg_basis_shfl<false>(alpha, v);
+      else epg_basis_shfl<true>(alpha, v);
+      gram_build(g + sl.pristine);
+      cursrc.G = Gs, cursrc.ldg = P.ldg, cursrc.Arm = g + sl.pristine, cursrc.Acm = g + sl.pristine_cm;
+    } else {
+      epg_basis(alpha, v);
+    }
+  }
+
   __device__ void fa_probe(int I, unsigned long long &seen, int &numeval) {
     double u, du;
-    fa_eval(I, u, du);
+    if constexpr (GRAM) fa_eval_gram(I, u, du);
+    else fa_eval(I, u, du);
     if (lane == 0) g[sl.fa_u + I] = u, g[sl.fa_du + I] = du;
     __syncwarp();
     seen |= (1ull << I);
@@ -335,9 +380,17 @@ struct Warp {
 
   // ================= regularised solves =================
   __device__ __noinline__ NnlsOut solve_unreg(const double *Asrc) {
-    stage_matrix(Asrc);
-    nnls_warm_start<false>(ws, bd, 0.0, 0);
-    return nnls_core<false>(ws, 0.0);
+    if constexpr (GRAM) {
+      GramOut go;
+      NnlsOut o;
+      o.rnorm_sq = gram_solve_unreg(cursrc, go);
+      o.xnorm_sq = go.xnorm_sq, o.nsetp = go.k, o.rows_used = 0;
+      return o;
+    } else {
+      stage_matrix(Asrc);
+      nnls_warm_start<false>(ws, bd, 0.0, 0);
+      return nnls_core<false>(ws, 0.0);
+    }
   }
 
   // solve!(cache, mu)  src/lsqnonneg.jl:417-444 — exact-mu hit or solve into the next slot
@@ -346,6 +399,10 @@ struct Warp {
     __syncwarp();
   }
   __device__ __noinline__ void cache_solve(double mu, const double *Asrc) {
+    if constexpr (GRAM) {
+      cache_solve_gram(mu, cursrc);
+      return;
+    }
     int hit = -1, firstnan = -1;
     for (int i = 0; i < DECAES_NCACHE; i++) {
       double mui = slot_mu[i];
@@ -372,6 +429,7 @@ struct Warp {
   }
   __device__ __forceinline__ double cur_seminorm_sq() const { return slot_x2[cur_slot]; }
   __device__ __forceinline__ double cur_resnorm_sq() const {  // src/lsqnonneg.jl:309-313
+    if constexpr (GRAM) return slot_r2[cur_slot];  // stored as the explicit ||Ax - b||^2
     double mu = slot_mu[cur_slot];
     double r = slot_r2[cur_slot] - __dmul_rn(__dmul_rn(mu, mu), slot_x2[cur_slot]);
     return r > 0 ? r : 0.0;
@@ -740,6 +798,273 @@ struct Warp {
     return x;
   }
 
+  // =====================================================================================
+  // Gram-form solver path (gram.cuh).  Per voxel the warp keeps G = A'A and c = A'b in shared
+  // memory; A itself stays in the warp's global scratch (L2) in both layouts and is only read for
+  // explicit residuals (||Ax - b||^2, iterative refinement, fitted curve).
+  // =====================================================================================
+  // c = A' bd  (lane <-> column, coalesced rows of the row-major matrix)
+  __device__ __noinline__ void gram_rhs(const double *Arm) {
+    const int nTE = P.nTE, ld = P.ld;
+    for (int j = lane; j < P.nT2; j += 32) {
+      double a0 = 0.0, a1 = 0.0;
+      int i = 0;
+      for (; i + 1 < nTE; i += 2) {
+        a0 = fma(Arm[i * ld + j], bd[i], a0);
+        a1 = fma(Arm[(i + 1) * ld + j], bd[i + 1], a1);
+      }
+      if (i < nTE) a0 = fma(Arm[i * ld + j], bd[i], a0);
+      cvec[j] = a0 + a1;
+    }
+    __syncwarp();
+  }
+
+  // explicit residual r = bd - A_P s (stored in `fit`), returns ||r||^2.  lane <-> echo.
+  __device__ __noinline__ double gram_residual(const double *Acm, int k) {
+    const int nTE = P.nTE;
+    double acc = 0.0;
+    for (int i = lane; i < nTE; i += 32) {
+      double a0 = bd[i], a1 = 0.0;
+      int t = 0;
+      for (; t + 1 < k; t += 2) {
+        a0 = fma(-Acm[gws.P[t] * nTE + i], gws.s[t], a0);
+        a1 = fma(-Acm[gws.P[t + 1] * nTE + i], gws.s[t + 1], a1);
+      }
+      if (t < k) a0 = fma(-Acm[gws.P[t] * nTE + i], gws.s[t], a0);
+      double r = a0 + a1;
+      fit[i] = r;
+      acc = fma(r, r, acc);
+    }
+    acc = warp_sum(acc);
+    __syncwarp();
+    return acc;
+  }
+
+  // one step of iterative refinement on the active set: s += (G_PP + mu2 I)^-1 (A_P' r - mu2 s),
+  // with r = bd - A_P s already in `fit`.  Restores QR-level accuracy of the normal-equation solve.
+  __device__ __noinline__ void gram_refine(const double *Acm, int k, double mu2) {
+    const int nTE = P.nTE;
+    double *M = gws.M;
+    // g_t = A[:,P[t]]' r - mu2 s_t      (lane <-> active column)
+    for (int t = lane; t < k; t += 32) {
+      const double *col = Acm + gws.P[t] * nTE;
+      double a0 = 0.0, a1 = 0.0;
+      int i = 0;
+      for (; i + 1 < nTE; i += 2) {
+        a0 = fma(col[i], fit[i], a0);
+        a1 = fma(col[i + 1], fit[i + 1], a1);
+      }
+      if (i < nTE) a0 = fma(col[i], fit[i], a0);
+      gws.t1[t] = fma(-mu2, gws.s[t], a0 + a1);
+    }
+    __syncwarp();
+    // v = M g
+    for (int t = lane; t < k; t += 32) {
+      const double *row = M + (t * (t + 1)) / 2;
+      double a = 0.0;
+      for (int u = 0; u <= t; u++) a = fma(row[u], gws.t1[u], a);
+      gws.t2[t] = a;
+    }
+    __syncwarp();
+    // s += M' v
+    for (int u = lane; u < k; u += 32) {
+      double a = 0.0;
+      for (int t = u; t < k; t++) a = fma(M[(t * (t + 1)) / 2 + u], gws.t2[t], a);
+      double sn = gws.s[u] + a;
+      gws.s[u] = sn;
+      gws.x[gws.P[u]] = sn;
+    }
+    __syncwarp();
+  }
+
+  // unregularised NNLS following the reference's cold-start path, polished by one refinement step;
+  // returns ||A x - b||^2 (explicit) and leaves r in `fit`, x in gws.x, the active set in gws.P.
+  __device__ __noinline__ double gram_solve_unreg(const Src &src, GramOut &o) {
+    GramProb pr;
+    pr.G = src.G, pr.ldg = src.ldg, pr.c = cvec, pr.mu2 = 0.0, pr.n = P.nT2;
+    pr.max_set = P.nTE < P.nT2 ? P.nTE : P.nT2;
+    o = gram_nnls(pr, gws, false, 0ull);
+    double r2 = gram_residual(src.Acm, o.k);
+    if (o.k > 0) {
+      gram_refine(src.Acm, o.k, 0.0);
+      r2 = gram_residual(src.Acm, o.k);
+    }
+    return r2;
+  }
+
+  // loss_with_grad!  src/splines.jl:1010-1041 on grid angle k
+  __device__ __noinline__ void fa_eval_gram(int kang, double &u, double &du) {
+    const int nTE = P.nTE, n = P.nT2;
+    Src src;
+    src.G = P.gram_set + (size_t)kang * n * P.ldg, src.ldg = P.ldg;
+    src.Arm = P.basis_rm + (size_t)kang * P.copy_elems;
+    src.Acm = P.basis_cm + (size_t)kang * nTE * n;
+    gram_rhs(src.Arm);
+    GramOut o;
+    u = gram_solve_unreg(src, o);
+    const double *dAk = P.dbasis_cm + (size_t)kang * nTE * n;
+    double acc = 0.0;
+    for (int i = lane; i < nTE; i += 32) {
+      double dax = 0.0;
+      for (int t = 0; t < o.k; t++)
+        if (gws.s[t] > 0.0) dax = fma(gws.s[t], dAk[gws.P[t] * nTE + i], dax);
+      acc = fma(dax, -fit[i], acc);  // A x - b = -r
+    }
+    du = 2.0 * warp_sum(acc);
+  }
+
+  // EPG basis at the fitted angle, phase states in registers: lane <-> state index, shifts are warp
+  // shuffles, four T2 components advance together for instruction-level parallelism.  Arithmetic per
+  // state update follows epg_impulse_response! (src/EPGdecaycurve.jl:948-1028) exactly; states outside
+  // the reference's truncated range are simply carried along (they never feed back for ETL <= 63,
+  // resp. <= 127 with the second register set).
+  template <bool TWO>
+  __device__ __noinline__ void epg_basis_shfl(double alpha_deg, long long v) {
+    const int ETL = P.nTE, n = P.nT2, ld = P.ld;
+    double *prm = g + sl.pristine, *pcm = g + sl.pristine_cm;
+    double sina, cosa;
+    sincos(alpha_deg * 0.017453292519943295, &sina, &cosa);
+    const double m0 = sind_0_180(alpha_deg / 2);
+    const double E1 = P.E1;
+    constexpr int NS = TWO ? 2 : 1;
+    for (int j0 = 0; j0 < n; j0 += 4) {
+      double a[4], b[4], c[4], d[4], cp[4];
+      double F[NS][4], Fb[NS][4], Z[NS][4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int j = (j0 + q < n) ? j0 + q : n - 1;
+        const double E2 = P.E2[j];
+        const double E2h = __dmul_rn(E2, E2) / 2, E1E2 = __dmul_rn(E1, E2), E1sq = __dmul_rn(E1, E1);
+        a[q] = E2h, b[q] = __dmul_rn(E2h, cosa), c[q] = __dmul_rn(E1E2, sina), d[q] = __dmul_rn(E1sq, cosa);
+        cp[q] = -c[q] / 2;
+#pragma unroll
+        for (int sidx = 0; sidx < NS; sidx++) F[sidx][q] = 0.0, Fb[sidx][q] = 0.0, Z[sidx][q] = 0.0;
+        // state after the first echo (:966-968): state 1 = (a-b, 0, c'), state 2 = (a+b, 0, 0)
+        if (lane == 0) F[0][q] = __dsub_rn(a[q], b[q]), Z[0][q] = cp[q];
+        if (lane == 1) F[0][q] = __dadd_rn(a[q], b[q]);
+        if (lane == 0 && j0 + q < n) {
+          double val = fabs(__dmul_rn(m0, __dsub_rn(a[q], b[q])));
+          prm[0 * ld + j] = val, pcm[j * ETL + 0] = val;
+        }
+      }
+      for (int i = 2; i <= ETL; i++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          double vF[NS], vFb[NS], vZ[NS];
+#pragma unroll
+          for (int sidx = 0; sidx < NS; sidx++) {
+            double C = __dadd_rn(F[sidx][q], Fb[sidx][q]), Sd = __dsub_rn(F[sidx][q], Fb[sidx][q]);
+            double Cp = __dmul_rn(a[q], C), Sp = __dmul_rn(b[q], Sd);
+            if (i < ETL || sidx > 0) {
+              vFb[sidx] = fma(-c[q], Z[sidx][q], __dsub_rn(Cp, Sp));
+            } else {
+              vFb[sidx] = fma(-c[q], Z[sidx][q], fma(a[q], C, __dmul_rn(-b[q], Sd)));  // last echo, :1024
+            }
+            vF[sidx] = fma(c[q], Z[sidx][q], __dadd_rn(Cp, Sp));
+            vZ[sidx] = fma(cp[q], Sd, __dmul_rn(d[q], Z[sidx][q]));
+          }
+          // echo amplitude = new F of state 1
+          if (lane == 0 && j0 + q < n) {
+            double val = fabs(__dmul_rn(m0, vFb[0]));
+            prm[(i - 1) * ld + j0 + q] = val, pcm[(j0 + q) * ETL + (i - 1)] = val;
+          }
+          // shifts: F moves up one state, Fbar moves down one state, Z stays
+          double upF0 = __shfl_up_sync(DECAES_FULL_MASK, vF[0], 1);
+          double dnFb0 = __shfl_down_sync(DECAES_FULL_MASK, vFb[0], 1);
+          if (TWO) {
+            double upF1 = __shfl_up_sync(DECAES_FULL_MASK, vF[NS - 1], 1);
+            double wrapF = __shfl_sync(DECAES_FULL_MASK, vF[0], 31);        // state 32 -> state 33
+            double dnFb1 = __shfl_down_sync(DECAES_FULL_MASK, vFb[NS - 1], 1);
+            double wrapFb = __shfl_sync(DECAES_FULL_MASK, vFb[NS - 1], 0);  // state 33 -> state 32
+            F[NS - 1][q] = (lane == 0) ? wrapF : upF1;
+            Fb[NS - 1][q] = (lane == 31) ? 0.0 : dnFb1;
+            Z[NS - 1][q] = vZ[NS - 1];
+            Fb[0][q] = (lane == 31) ? wrapFb : dnFb0;
+          } else {
+            Fb[0][q] = (lane == 31) ? 0.0 : dnFb0;
+          }
+          F[0][q] = (lane == 0) ? vFb[0] : upF0;
+          Z[0][q] = vZ[0];
+        }
+      }
+    }
+    __syncwarp();
+    if (P.decaybasis && !P.fixed_alpha) {
+      for (int k = lane; k < ETL * n; k += 32) P.decaybasis[v + (long long)k * P.stride] = pcm[k];
+    }
+  }
+
+  // G = A'A and c = A'bd from the row-major basis in global scratch into shared memory.
+  // lane <-> column q, four rows p of G at a time.
+  __device__ __noinline__ void gram_build(const double *Arm) {
+    const int nTE = P.nTE, n = P.nT2, ld = P.ld, ldg = P.ldg;
+    for (int p0 = 0; p0 < n; p0 += 4) {
+      double acc[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[q][0] = acc[q][1] = 0.0;
+      const int q0 = lane, q1 = lane + 32;
+      for (int i = 0; i < nTE; i++) {
+        const double *row = Arm + i * ld;
+        const double aq0 = (q0 < n) ? row[q0] : 0.0, aq1 = (q1 < n) ? row[q1] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const double ap = row[(p0 + q < n) ? p0 + q : n - 1];
+          acc[q][0] = fma(ap, aq0, acc[q][0]);
+          acc[q][1] = fma(ap, aq1, acc[q][1]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (p0 + q < n) {
+          if (q0 < n) Gs[(p0 + q) * ldg + q0] = acc[q][0];
+          if (q1 < n) Gs[(p0 + q) * ldg + q1] = acc[q][1];
+        }
+    }
+    __syncwarp();
+    gram_rhs(Arm);
+  }
+
+  // solve!(cache, mu) for the Gram solver: exact-mu hit, else warm-start from the nearest cached mu
+  __device__ __noinline__ void cache_solve_gram(double mu, const Src &src) {
+    const int n = P.nT2;
+    int hit = -1, firstnan = -1, nearest = -1;
+    double dbest = CUDART_INF;
+    for (int i = 0; i < DECAES_NCACHE; i++) {
+      double mui = slot_mu[i];
+      if (isnan(mui)) {
+        if (firstnan < 0) firstnan = i;
+      } else if (mu == mui) {
+        hit = i;
+        break;
+      } else {
+        double dd = fabs(log(mu) - log(mui));
+        if (dd < dbest && slot_mask[i] != 0ull) dbest = dd, nearest = i;
+      }
+    }
+    if (hit >= 0) {
+      cur_slot = hit;
+      return;
+    }
+    cur_slot = (firstnan >= 0) ? firstnan : (cur_slot + 1) % DECAES_NCACHE;
+    GramProb pr;
+    pr.G = src.G, pr.ldg = src.ldg, pr.c = cvec, pr.mu2 = __dmul_rn(mu, mu), pr.n = n, pr.max_set = n;
+    GramOut o;
+    if (nearest >= 0) {
+      const double *sx = g + sl.slots_x + nearest * n;
+      for (int j = lane; j < n; j += 32) gws.x[j] = sx[j];
+      __syncwarp();
+      o = gram_nnls(pr, gws, true, slot_mask[nearest]);
+    } else {
+      o = gram_nnls(pr, gws, false, 0ull);
+    }
+    double r2 = gram_residual(src.Acm, o.k);
+    double *sx = g + sl.slots_x + cur_slot * n;
+    for (int j = lane; j < n; j += 32) sx[j] = gws.x[j];
+    if (lane == 0)
+      slot_mu[cur_slot] = mu, slot_r2[cur_slot] = r2, slot_x2[cur_slot] = o.xnorm_sq, slot_mask[cur_slot] = o.mask;
+    __syncwarp();
+  }
+
   // ================= one voxel =================
   __device__ __noinline__ void process(long long v, const double *signal /* smem, nTE */) {
     const int nTE = P.nTE, n = P.nT2;
@@ -758,14 +1083,18 @@ struct Warp {
     const double *Asrc;
     if (P.alpha_provided) {
       alpha = P.alpha[v];
-      epg_basis(alpha, v);
+      basis_at(alpha, v);
       Asrc = g + sl.pristine;
     } else if (P.fixed_alpha) {
       alpha = P.SetFlipAngle;
       Asrc = P.basis_rm;
+      if constexpr (GRAM) {
+        cursrc.G = P.gram_set, cursrc.ldg = P.ldg, cursrc.Arm = P.basis_rm, cursrc.Acm = P.basis_cm;
+        gram_rhs(cursrc.Arm);
+      }
     } else {
       alpha = optimize_flip_angle();
-      epg_basis(alpha, v);
+      basis_at(alpha, v);
       Asrc = g + sl.pristine;
     }
 
@@ -858,23 +1187,43 @@ struct Warp {
         xs[j] = __dmul_rn(xv, max_signal);
       }
     }
-    stage_matrix(Asrc);  // pristine basis back into shared memory for fit = A x
     double r2 = 0.0, rs = 0.0;
-    for (int i = lane; i < nTE; i += 32) {
-      const double *row = ws.A + i * P.ld;
-      double s = 0.0;
-      for (int j = 0; j < n; j++) s = fma(row[j], xs[j], s);
-      fit[i] = s;
-      double res = s - __dmul_rn(bd[i], max_signal);
-      ws.u[i] = res;
-      r2 = fma(res, res, r2);
-      rs += res;
+    // residual scratch: the QR path has the Householder vector buffer; the Gram path borrows the
+    // L-curve point cache in global scratch, which is free by now (4 * DECAES_LC_MAX >= nTE doubles)
+    double *resv = GRAM ? (g + sl.lc_pts) : ws.u;
+    if constexpr (GRAM) {
+      const double *Acm = cursrc.Acm;
+      for (int i = lane; i < nTE; i += 32) {
+        double s0 = 0.0;
+        for (int j = 0; j < n; j++) {
+          double xj = xs[j];
+          if (xj != 0.0) s0 = fma(Acm[j * nTE + i], xj, s0);
+        }
+        fit[i] = s0;
+        double res = s0 - __dmul_rn(bd[i], max_signal);
+        resv[i] = res;
+        r2 = fma(res, res, r2);
+        rs += res;
+      }
+    } else {
+      stage_matrix(Asrc);  // pristine basis back into shared memory for fit = A x
+      for (int i = lane; i < nTE; i += 32) {
+        const double *row = ws.A + i * P.ld;
+        double s0 = 0.0;
+        for (int j = 0; j < n; j++) s0 = fma(row[j], xs[j], s0);
+        fit[i] = s0;
+        double res = s0 - __dmul_rn(bd[i], max_signal);
+        resv[i] = res;
+        r2 = fma(res, res, r2);
+        rs += res;
+      }
     }
+    __syncwarp();
     r2 = warp_sum(r2);
     double mean = warp_sum(rs) / nTE;
     double var = 0.0;
     for (int i = lane; i < nTE; i += 32) {
-      double dlt = ws.u[i] - mean;
+      double dlt = resv[i] - mean;
       var = fma(dlt, dlt, var);
     }
     var = warp_sum(var);

@@ -54,7 +54,7 @@ def compare(ref, got, scalars=("alpha", "sfr", "ggm"), extra=("gdn", "gva", "fnr
         m0, m1 = np.asarray(ref["mu"], dtype=float), np.asarray(got["mu"], dtype=float)
         with np.errstate(invalid="ignore", divide="ignore"):
             dlog = np.abs(np.log(m0) - np.log(m1))
-        same = (m0 == m1) | (np.isnan(m0) & np.isnan(m1)) | (dlog <= 1e-9)
+        same = (m0 == m1) | (np.isnan(m0) & np.isnan(m1)) | (dlog <= 1e-7)
         flip = ~same
         rep["mu_flips"] = int(flip.sum())
         rep["mu_flip_frac"] = float(flip.mean()) if nvox else 0.0
