@@ -116,7 +116,7 @@ __global__ void basis_setup_kernel(const __grid_constant__ SetupParams S) {
 }
 
 // G_k = A_k' A_k for every grid angle (Gram solver): one thread per (k, p, q)
-__global__ void gram_setup_kernel(const __grid_constant__ SetupParams S, double *gram_set, int ldg) {
+__global__ void gram_setup_kernel(const __grid_constant__ SetupParams S, double *gram_set, int ldg, int gstride) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int n = S.nT2;
   if (t >= (long long)S.nA * n * n) return;
@@ -129,7 +129,7 @@ __global__ void gram_setup_kernel(const __grid_constant__ SetupParams S, double 
     a1 = fma(rm[(i + 1) * S.ld + p], rm[(i + 1) * S.ld + q], a1);
   }
   if (i < S.nTE) a0 = fma(rm[i * S.ld + p], rm[i * S.ld + q], a0);
-  gram_set[(size_t)k * n * ldg + p * ldg + q] = a0 + a1;
+  gram_set[(size_t)k * gstride + p * ldg + q] = a0 + a1;
 }
 
 template <bool GRAM>
@@ -475,7 +475,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   // solver variant: normal-equation active set (default) or the QR port (DECAES_SOLVER=qr, kept for A/B checks)
   const char *sv = getenv("DECAES_SOLVER");
   P.gram = !(sv && strcmp(sv, "qr") == 0);
-  P.ldg = nT2 | 1;
+  P.ldg = (nT2 + 1) | 1;  // one array holds the lower triangle of G and, above it, M = L^-1 (gram.cuh)
   if (P.gram) P.a_elems = nT2 * P.ldg;
   P.a_elems = (P.a_elems + 1) & ~1;
   P.fixed_alpha = fixed, P.alpha_provided = o->alpha_provided;
@@ -540,7 +540,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     ws.basis_cm_cap = cm;
   }
   if ((rc = ensure(&ws.scratch, &ws.scratch_cap, (size_t)plan->grid * sl.total))) return rc;
-  if ((rc = ensure(&ws.gram_set, &ws.gram_cap, (size_t)nA * nT2 * P.ldg))) return rc;
+  if ((rc = ensure(&ws.gram_set, &ws.gram_cap, (size_t)nA * P.a_elems))) return rc;
   P.gram_set = ws.gram_set;
   if (!ws.counters) CUDA_TRY(cudaMalloc(&ws.counters, 8 * sizeof(unsigned long long)));
   for (int i = 0; i < 4; i++)
@@ -581,7 +581,8 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
   CUDA_TRY(cudaGetLastError());
   if (P.gram) {
     long long ng = (long long)plan.S.nA * plan.S.nT2 * plan.S.nT2;
-    gram_setup_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, stream>>>(plan.S, ws.gram_set, P.ldg);
+    CUDA_TRY(cudaMemsetAsync(ws.gram_set, 0, sizeof(double) * (size_t)plan.S.nA * P.a_elems, stream));
+    gram_setup_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, stream>>>(plan.S, ws.gram_set, P.ldg, P.a_elems);
     CUDA_TRY(cudaGetLastError());
   }
   CUDA_TRY(cudaEventRecord(ws.ev[1], stream));

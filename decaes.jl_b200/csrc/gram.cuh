@@ -6,23 +6,27 @@
 // identical feasibility step / removal rule and 3n iteration cap.  What changes is the linear
 // algebra underneath: instead of reflecting the whole nTE x nT2 matrix for every pivot (a BLAS-2
 // sweep over ~18 KB of shared memory per pivot), the warp keeps
-//     G = A'A (+ mu^2 I)   n x n, shared memory (per voxel) or L2 (per flip-angle grid point)
+//     G = A'A (+ mu^2 I)   n x n symmetric
 //     c = A'b              n
-//     M = L^-1             inverse Cholesky factor of G_PP in pivot order, packed lower triangle
+//     M = L^-1             inverse Cholesky factor of G_PP in pivot order
 // so that appending a column is two O(k) fma chains per lane plus two warp reductions, the
 // solution is s = M'(M c_P) maintained incrementally, and the dual is w = c - G_P x_P.
 // The minimiser of the Tikhonov problems (mu > 0) is unique, so those solves may be warm-started
 // from the active set of the nearest mu already solved; unregularised solves follow the
 // reference's cold-start path pivot by pivot and are polished with one step of iterative
 // refinement on the explicit residual (done by the caller, which owns A).
+//
+// Shared-memory layout: ONE n x ld array T (ld = (n+1)|1, odd => both access directions are
+// bank-conflict free) holds the lower triangle of G and, in the strictly-upper part, M:
+//     G(p,q) = T[max(p,q)*ld + min(p,q)]          M(t,u) = T[u*ld + t + 1]   (u <= t)
 #pragma once
 #include "common.cuh"
 
 namespace decaes {
 
 struct GramProb {
-  const double *G;  // n x n symmetric, row-major, leading dimension ldg (shared or global memory)
-  int ldg;
+  double *T;        // combined G / M array in shared memory
+  int ld;
   const double *c;  // [n] shared memory
   double mu2;       // mu^2 (0 for the plain problem)
   int n;
@@ -30,7 +34,6 @@ struct GramProb {
 };
 
 struct GramWs {  // shared-memory scratch of one warp
-  double *M;     // packed lower triangle [n(n+1)/2]: M[t][u] at t(t+1)/2 + u
   double *y;     // [n] y = M c_P
   double *s;     // [n] s = M' y   (solution on P, in pivot order)
   double *x;     // [n] current feasible solution, indexed by column
@@ -46,56 +49,75 @@ struct GramOut {
   double xnorm_sq;           // sum of squares of the solution
 };
 
-#define GM(t, u) M[((t) * ((t) + 1)) / 2 + (u)]
+__device__ __forceinline__ double gram_G(const GramProb &p, int a, int b) {
+  int hi = a > b ? a : b, lo = a > b ? b : a;
+  return p.T[hi * p.ld + lo];
+}
+#define GM_(t, u) T[(u) * ld + (t) + 1]
+
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
+  unsigned lo = __reduce_or_sync(DECAES_FULL_MASK, (unsigned)v);
+  unsigned hi = __reduce_or_sync(DECAES_FULL_MASK, (unsigned)(v >> 32));
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long mask_of(const int *P, int k) {
+  const int lane = lane_id();
+  unsigned long long m = 0ull;
+  if (lane < k) m |= 1ull << P[lane];
+  if (lane + 32 < k) m |= 1ull << P[lane + 32];
+  return warp_or64(m);
+}
 
 // Append column j to the factorisation (pivot position k).  Returns false (and changes nothing)
 // when the column is numerically dependent (d^2 <= 0) or, with `need_positive`, when its
 // coefficient would not be positive (the reference's b1/A1 > 0 test).
 __device__ __noinline__ bool gram_append(const GramProb &p, const GramWs &ws, int &k, int j, bool need_positive) {
   const int lane = lane_id();
-  double *M = ws.M;
-  // g_t = G[P[t]][j]
-  for (int t = lane; t < k; t += 32) ws.t1[t] = p.G[ws.P[t] * p.ldg + j];
+  double *T = p.T;
+  const int ld = p.ld;
+  for (int t = lane; t < k; t += 32) ws.t1[t] = gram_G(p, ws.P[t], j);
   __syncwarp();
-  // l = M g  (lane <-> row t)
+  // l = M g  (lane <-> row t; for fixed u the lanes read consecutive words)
   double ll = 0.0, ly = 0.0;
   for (int t = lane; t < k; t += 32) {
-    const double *row = M + (t * (t + 1)) / 2;
-    double a0 = 0.0, a1 = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int u = 0;
-    for (; u + 1 <= t; u += 2) {
-      a0 = fma(row[u], ws.t1[u], a0);
-      a1 = fma(row[u + 1], ws.t1[u + 1], a1);
+    for (; u + 3 <= t; u += 4) {
+      a0 = fma(GM_(t, u), ws.t1[u], a0);
+      a1 = fma(GM_(t, u + 1), ws.t1[u + 1], a1);
+      a2 = fma(GM_(t, u + 2), ws.t1[u + 2], a2);
+      a3 = fma(GM_(t, u + 3), ws.t1[u + 3], a3);
     }
-    if (u <= t) a0 = fma(row[u], ws.t1[u], a0);
-    double lt = a0 + a1;
+    for (; u <= t; u++) a0 = fma(GM_(t, u), ws.t1[u], a0);
+    double lt = (a0 + a1) + (a2 + a3);
     ws.t2[t] = lt;
     ll = fma(lt, lt, ll);
     ly = fma(lt, ws.y[t], ly);
   }
   ll = warp_sum(ll), ly = warp_sum(ly);
-  const double d2 = (p.G[j * p.ldg + j] + p.mu2) - ll;
+  const double d2 = (T[j * ld + j] + p.mu2) - ll;
   if (!(d2 > 0.0)) return false;
-  const double d = sqrt(d2), dinv = 1.0 / d;
+  const double dinv = rsqrt(d2);
   const double ynew = (p.c[j] - ly) * dinv;
   if (need_positive && !(ynew > 0.0)) return false;
   __syncwarp();
-  // new row of M: m_u = -dinv * sum_{t >= u} l_t M[t][u]   (lane <-> column u)
-  double *newrow = M + (k * (k + 1)) / 2;
+  // new row of M: M(k,u) = -dinv * sum_{t >= u} l_t M(t,u)   (lane <-> column u, own row contiguous in t)
   for (int u = lane; u < k; u += 32) {
-    double a0 = 0.0, a1 = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int t = u;
-    for (; t + 1 < k; t += 2) {
-      a0 = fma(ws.t2[t], GM(t, u), a0);
-      a1 = fma(ws.t2[t + 1], GM(t + 1, u), a1);
+    for (; t + 3 < k; t += 4) {
+      a0 = fma(ws.t2[t], GM_(t, u), a0);
+      a1 = fma(ws.t2[t + 1], GM_(t + 1, u), a1);
+      a2 = fma(ws.t2[t + 2], GM_(t + 2, u), a2);
+      a3 = fma(ws.t2[t + 3], GM_(t + 3, u), a3);
     }
-    if (t < k) a0 = fma(ws.t2[t], GM(t, u), a0);
-    double mu_ = -dinv * (a0 + a1);
-    newrow[u] = mu_;
+    for (; t < k; t++) a0 = fma(ws.t2[t], GM_(t, u), a0);
+    double mu_ = -dinv * ((a0 + a1) + (a2 + a3));
+    GM_(k, u) = mu_;
     ws.s[u] = fma(ynew, mu_, ws.s[u]);
   }
   if (lane == 0) {
-    newrow[k] = dinv;
+    GM_(k, k) = dinv;
     ws.y[k] = ynew;
     ws.s[k] = ynew * dinv;
     ws.P[k] = j;
@@ -108,12 +130,12 @@ __device__ __noinline__ bool gram_append(const GramProb &p, const GramWs &ws, in
 // Rebuild rows [from, k) of M (after a removal or for a warm start); P[0:k) already holds the columns.
 __device__ __noinline__ void gram_rebuild(const GramProb &p, const GramWs &ws, int &k, int from) {
   const int lane = lane_id();
-  const int kold = k;
-  double *M = ws.M;
+  const int kold = k, ld = p.ld;
+  double *T = p.T;
   // s = M[0:from]' y[0:from]
   for (int u = lane; u < kold; u += 32) {
     double a = 0.0;
-    for (int t = u; t < from; t++) a = fma(GM(t, u), ws.y[t], a);
+    for (int t = u; t < from; t++) a = fma(GM_(t, u), ws.y[t], a);
     ws.s[u] = a;
   }
   __syncwarp();
@@ -123,28 +145,26 @@ __device__ __noinline__ void gram_rebuild(const GramProb &p, const GramWs &ws, i
     __syncwarp();
     if (!gram_append(p, ws, k, j, false)) {
       // numerically dependent column inside a set that was independent a moment ago: drop it
-      if (lane == 0) {
-        ws.x[j] = 0.0;
-      }
+      if (lane == 0) ws.x[j] = 0.0;
       __syncwarp();
     }
-    // gram_append wrote P[k-1] = j at the compacted position; later entries are still at t+1..
   }
 }
 
-// w_j = c_j - sum_t G[P[t]][j] * xs_t  for every column (the entries of active columns are forced to 0).
-// xs = coefficients in pivot order (ws.s after a solve).
+// w_j = c_j - sum_t G(P[t], j) * s_t for every column; entries of active columns are forced to 0.
 __device__ __noinline__ void gram_dual(const GramProb &p, const GramWs &ws, int k, unsigned long long mask) {
   const int lane = lane_id();
   for (int j = lane; j < p.n; j += 32) {
-    double a0 = p.c[j], a1 = 0.0;
+    double a0 = p.c[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int t = 0;
-    for (; t + 1 < k; t += 2) {
-      a0 = fma(-p.G[ws.P[t] * p.ldg + j], ws.s[t], a0);
-      a1 = fma(-p.G[ws.P[t + 1] * p.ldg + j], ws.s[t + 1], a1);
+    for (; t + 3 < k; t += 4) {
+      a0 = fma(-gram_G(p, ws.P[t], j), ws.s[t], a0);
+      a1 = fma(-gram_G(p, ws.P[t + 1], j), ws.s[t + 1], a1);
+      a2 = fma(-gram_G(p, ws.P[t + 2], j), ws.s[t + 2], a2);
+      a3 = fma(-gram_G(p, ws.P[t + 3], j), ws.s[t + 3], a3);
     }
-    if (t < k) a0 = fma(-p.G[ws.P[t] * p.ldg + j], ws.s[t], a0);
-    ws.w[j] = ((mask >> j) & 1ull) ? 0.0 : a0 + a1;
+    for (; t < k; t++) a0 = fma(-gram_G(p, ws.P[t], j), ws.s[t], a0);
+    ws.w[j] = ((mask >> j) & 1ull) ? 0.0 : (a0 + a1) + (a2 + a3);
   }
   __syncwarp();
 }
@@ -161,10 +181,10 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
   if (!warm) {
     mask = 0ull;
     // dual as if the last column were active; w[n-1] = 0, or 1 if every other dual is <= 0
-    const double xj = p.c[n - 1] / (p.G[(n - 1) * p.ldg + (n - 1)] + p.mu2);
+    const double xj = p.c[n - 1] / (p.T[(n - 1) * p.ld + (n - 1)] + p.mu2);
     bool anypos = false;
     for (int j = lane; j < n; j += 32) {
-      double wj = (j < n - 1) ? fma(-p.G[(n - 1) * p.ldg + j], xj, p.c[j]) : 0.0;
+      double wj = (j < n - 1) ? fma(-gram_G(p, n - 1, j), xj, p.c[j]) : 0.0;
       ws.w[j] = wj;
       ws.x[j] = 0.0;
       anypos |= !(wj <= 0.0);
@@ -186,10 +206,7 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
     __syncwarp();
     k = kk;
     gram_rebuild(p, ws, k, 0);
-    if (k != kk) {  // a column was dropped as dependent: rebuild the mask
-      mask = 0ull;
-      for (int t = 0; t < k; t++) mask |= 1ull << ws.P[t];
-    }
+    if (k != kk) mask = mask_of(ws.P, k);  // a column was dropped as dependent
     need_solve_check = (k > 0);
     if (k == 0) {
       for (int j = lane; j < n; j += 32) ws.w[j] = p.c[j];
@@ -259,7 +276,6 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
           ws.x[jr] = 0.0;
           for (int t = imv; t < k - 1; t++) ws.P[t] = ws.P[t + 1];
         }
-        mask &= ~(1ull << ws.P[imv]);  // evaluated before lane 0's shift is visible? see below
         __syncwarp();
         k -= 1;
         if (imv < first_removed) first_removed = imv;
@@ -269,16 +285,8 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
         else if (bad1) imv = 32 + __ffs(bad1) - 1;
         else break;
       }
-      // rebuild the mask from P (cheap, avoids ordering hazards) and the factor from the first hole
-      mask = 0ull;
-      for (int t = 0; t < k; t++) mask |= 1ull << ws.P[t];
-      int knew = k;
-      gram_rebuild(p, ws, knew, first_removed);
-      if (knew != k) {
-        k = knew;
-        mask = 0ull;
-        for (int t = 0; t < k; t++) mask |= 1ull << ws.P[t];
-      }
+      gram_rebuild(p, ws, k, first_removed);
+      mask = mask_of(ws.P, k);
     }
     if (terminated) break;
 
@@ -295,7 +303,5 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
   o.xnorm_sq = warp_sum(acc);
   return o;
 }
-
-#undef GM
 
 }  // namespace decaes

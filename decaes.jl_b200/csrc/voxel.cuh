@@ -69,10 +69,10 @@ struct SmemLayout {
   int M, c, y, s, t1, t2;  // Gram solver only
   __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems, int gram) {
     int o = 0;
-    A = o, o += a_elems;  // QR: working matrix / EPG scratch.  Gram: G (nT2 x ldg)
+    A = o, o += a_elems;  // QR: working matrix / EPG scratch.  Gram: combined G / M array (nT2 x ldg)
     b = u = M = c = y = s = t1 = t2 = 0;
     if (gram) {
-      M = o, o += (nT2 * (nT2 + 1)) / 2;
+      M = 0;  // M lives in the strictly-upper part of the G array (gram.cuh)
       c = o, o += nT2;
       y = o, o += nT2;
       s = o, o += nT2;
@@ -129,7 +129,7 @@ struct Warp {
     ws.idx = (int *)(smem + L.idx);
     ws.ld = p.ld, ws.n = p.nT2, ws.m0 = p.nTE;
     Gs = smem + L.A, cvec = smem + L.c;
-    gws.M = smem + L.M, gws.y = smem + L.y, gws.s = smem + L.s, gws.x = smem + L.x, gws.w = smem + L.w;
+    gws.y = smem + L.y, gws.s = smem + L.s, gws.x = smem + L.x, gws.w = smem + L.w;
     gws.t1 = smem + L.t1, gws.t2 = smem + L.t2, gws.P = (int *)(smem + L.idx);
     slot_mask = (unsigned long long *)(smem + L.slot_mask);
     bd = smem + L.bd, sig = smem + L.sig, fit = smem + L.fit;
@@ -150,6 +150,18 @@ struct Warp {
     if (lane == 0) {
       mbar_expect_tx(bar, (unsigned)(P.copy_elems * 8));
       tma_bulk_g2s(ws.A, src, (unsigned)(P.copy_elems * 8), bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+  }
+
+  // TMA bulk copy of `bytes` (multiple of 16) from global to shared memory, whole warp waits
+  __device__ __noinline__ void stage_bulk(void *dst, const void *src, unsigned bytes) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_expect_tx(bar, bytes);
+      tma_bulk_g2s(dst, src, bytes, bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -844,7 +856,8 @@ struct Warp {
   // with r = bd - A_P s already in `fit`.  Restores QR-level accuracy of the normal-equation solve.
   __device__ __noinline__ void gram_refine(const double *Acm, int k, double mu2) {
     const int nTE = P.nTE;
-    double *M = gws.M;
+    double *T = Gs;
+    const int ld = P.ldg;
     // g_t = A[:,P[t]]' r - mu2 s_t      (lane <-> active column)
     for (int t = lane; t < k; t += 32) {
       const double *col = Acm + gws.P[t] * nTE;
@@ -860,16 +873,15 @@ struct Warp {
     __syncwarp();
     // v = M g
     for (int t = lane; t < k; t += 32) {
-      const double *row = M + (t * (t + 1)) / 2;
       double a = 0.0;
-      for (int u = 0; u <= t; u++) a = fma(row[u], gws.t1[u], a);
+      for (int u = 0; u <= t; u++) a = fma(GM_(t, u), gws.t1[u], a);
       gws.t2[t] = a;
     }
     __syncwarp();
     // s += M' v
     for (int u = lane; u < k; u += 32) {
       double a = 0.0;
-      for (int t = u; t < k; t++) a = fma(M[(t * (t + 1)) / 2 + u], gws.t2[t], a);
+      for (int t = u; t < k; t++) a = fma(GM_(t, u), gws.t2[t], a);
       double sn = gws.s[u] + a;
       gws.s[u] = sn;
       gws.x[gws.P[u]] = sn;
@@ -881,7 +893,7 @@ struct Warp {
   // returns ||A x - b||^2 (explicit) and leaves r in `fit`, x in gws.x, the active set in gws.P.
   __device__ __noinline__ double gram_solve_unreg(const Src &src, GramOut &o) {
     GramProb pr;
-    pr.G = src.G, pr.ldg = src.ldg, pr.c = cvec, pr.mu2 = 0.0, pr.n = P.nT2;
+    pr.T = Gs, pr.ld = P.ldg, pr.c = cvec, pr.mu2 = 0.0, pr.n = P.nT2;
     pr.max_set = P.nTE < P.nT2 ? P.nTE : P.nT2;
     o = gram_nnls(pr, gws, false, 0ull);
     double r2 = gram_residual(src.Acm, o.k);
@@ -896,9 +908,10 @@ struct Warp {
   __device__ __noinline__ void fa_eval_gram(int kang, double &u, double &du) {
     const int nTE = P.nTE, n = P.nT2;
     Src src;
-    src.G = P.gram_set + (size_t)kang * n * P.ldg, src.ldg = P.ldg;
+    src.G = P.gram_set + (size_t)kang * P.a_elems, src.ldg = P.ldg;
     src.Arm = P.basis_rm + (size_t)kang * P.copy_elems;
     src.Acm = P.basis_cm + (size_t)kang * nTE * n;
+    stage_bulk(Gs, src.G, (unsigned)(P.a_elems * 8));  // TMA: G_k (lower triangle valid) -> shared memory
     gram_rhs(src.Arm);
     GramOut o;
     u = gram_solve_unreg(src, o);
@@ -999,26 +1012,21 @@ struct Warp {
   __device__ __noinline__ void gram_build(const double *Arm) {
     const int nTE = P.nTE, n = P.nT2, ld = P.ld, ldg = P.ldg;
     for (int p0 = 0; p0 < n; p0 += 4) {
-      double acc[4][2];
+      const int qmax = (p0 + 3 < n) ? p0 + 3 : n - 1;  // only q <= p is stored
+      for (int qb = 0; qb <= qmax; qb += 32) {
+        const int q = qb + lane;
+        const bool act = q <= qmax;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < nTE; i++) {
+          const double *row = Arm + i * ld;
+          const double aq = act ? row[q] : 0.0;
 #pragma unroll
-      for (int q = 0; q < 4; q++) acc[q][0] = acc[q][1] = 0.0;
-      const int q0 = lane, q1 = lane + 32;
-      for (int i = 0; i < nTE; i++) {
-        const double *row = Arm + i * ld;
-        const double aq0 = (q0 < n) ? row[q0] : 0.0, aq1 = (q1 < n) ? row[q1] : 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const double ap = row[(p0 + q < n) ? p0 + q : n - 1];
-          acc[q][0] = fma(ap, aq0, acc[q][0]);
-          acc[q][1] = fma(ap, aq1, acc[q][1]);
+          for (int r = 0; r < 4; r++) acc[r] = fma(row[(p0 + r < n) ? p0 + r : n - 1], aq, acc[r]);
         }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if (act && p0 + r < n && q <= p0 + r) Gs[(p0 + r) * ldg + q] = acc[r];
       }
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        if (p0 + q < n) {
-          if (q0 < n) Gs[(p0 + q) * ldg + q0] = acc[q][0];
-          if (q1 < n) Gs[(p0 + q) * ldg + q1] = acc[q][1];
-        }
     }
     __syncwarp();
     gram_rhs(Arm);
@@ -1037,7 +1045,7 @@ struct Warp {
         hit = i;
         break;
       } else {
-        double dd = fabs(log(mu) - log(mui));
+        double dd = mu > mui ? mu / mui : mui / mu;  // monotone in |log mu - log mui|
         if (dd < dbest && slot_mask[i] != 0ull) dbest = dd, nearest = i;
       }
     }
@@ -1047,7 +1055,7 @@ struct Warp {
     }
     cur_slot = (firstnan >= 0) ? firstnan : (cur_slot + 1) % DECAES_NCACHE;
     GramProb pr;
-    pr.G = src.G, pr.ldg = src.ldg, pr.c = cvec, pr.mu2 = __dmul_rn(mu, mu), pr.n = n, pr.max_set = n;
+    pr.T = Gs, pr.ld = P.ldg, pr.c = cvec, pr.mu2 = __dmul_rn(mu, mu), pr.n = n, pr.max_set = n;
     GramOut o;
     if (nearest >= 0) {
       const double *sx = g + sl.slots_x + nearest * n;
@@ -1090,6 +1098,7 @@ struct Warp {
       Asrc = P.basis_rm;
       if constexpr (GRAM) {
         cursrc.G = P.gram_set, cursrc.ldg = P.ldg, cursrc.Arm = P.basis_rm, cursrc.Acm = P.basis_cm;
+        stage_bulk(Gs, P.gram_set, (unsigned)(P.a_elems * 8));
         gram_rhs(cursrc.Arm);
       }
     } else {
