@@ -12,18 +12,27 @@
 #define DECAES_LC_MAX 96       // L-curve point / state cache capacity per voxel
 #define DECAES_NCACHE 8        // NNLSTikhonovRegProblemCache slots (src/lsqnonneg.jl:396)
 #define DECAES_GROUP 4         // voxels fetched per work item = one 32-byte sector per echo
+#define DECAES_MAX_WARPS 12    // warps per persistent CTA (register file: 65536 / (12*32) = 170 regs/thread)
 
 namespace decaes {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Out-of-line math: the pipeline kernel is I-cache bound (ncu: stall_no_inst), so the software
+// sequences behind double-precision div / sqrt / log / exp are kept as single shared copies.
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+__device__ __noinline__ double drsqrt(double a) { return rsqrt(a); }
+__device__ __noinline__ double dlog(double a) { return log(a); }
+__device__ __noinline__ double dexp(double a) { return exp(a); }
+
 // Butterfly sums: every lane ends with the bitwise-identical total (addition commutes).
-__device__ __forceinline__ double warp_sum(double v) {
+__device__ __noinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DECAES_FULL_MASK, v, o);
   return v;
 }
-__device__ __forceinline__ double warp_max(double v) {
+__device__ __noinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(DECAES_FULL_MASK, v, o));
   return v;
@@ -32,7 +41,7 @@ __device__ __forceinline__ double warp_bcast(double v, int src) { return __shfl_
 
 // (value, index) reductions with "first index wins on ties", matching sequential scans
 // that replace only on strict comparison.
-__device__ __forceinline__ void warp_argmax_first(double &v, int &i) {
+__device__ __noinline__ void warp_argmax_first(double &v, int &i) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double ov = __shfl_xor_sync(DECAES_FULL_MASK, v, o);
@@ -40,7 +49,7 @@ __device__ __forceinline__ void warp_argmax_first(double &v, int &i) {
     if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
   }
 }
-__device__ __forceinline__ void warp_argmin_first(double &v, int &i) {
+__device__ __noinline__ void warp_argmin_first(double &v, int &i) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double ov = __shfl_xor_sync(DECAES_FULL_MASK, v, o);

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -132,11 +133,18 @@ __global__ void gram_setup_kernel(const __grid_constant__ SetupParams S, double 
   gram_set[(size_t)k * gstride + p * ldg + q] = a0 + a1;
 }
 
+// Persistent CTAs of P.warps_per_cta warps, one CTA per SM.  Every warp owns a slice of the dynamic
+// shared memory and processes its own voxels; CTA barriers keep the warps in the same PHASE of the
+// per-voxel chain (flip-angle fit | EPG basis | regularised solve + outputs).  The kernel is
+// instruction-cache bound (ncu: stall_no_inst dominates when warps wander through ~170 KB of hot
+// code independently), and warps that execute the same phase share its cache lines.
 template <bool GRAM>
-__global__ void __launch_bounds__(32) voxel_pipeline_kernel(const __grid_constant__ PipeParams P) {
+__global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kernel(const __grid_constant__ PipeParams P) {
   extern __shared__ __align__(128) double smem[];
-  double *gscratch = P.scratch + (size_t)blockIdx.x * P.scratch_per_warp;
-  Warp<GRAM> W(P, smem, gscratch);
+  const int wid = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + wid;
+  double *gscratch = P.scratch + (size_t)gwarp * P.scratch_per_warp;
+  Warp<GRAM> W(P, smem + (size_t)wid * (P.smem_per_warp / 8), gscratch);
   const int lane = lane_id();
   if (lane == 0) {
     mbar_init(W.bar, 1);
@@ -147,29 +155,44 @@ __global__ void __launch_bounds__(32) voxel_pipeline_kernel(const __grid_constan
 
   const long long ngroups = (P.nvox + DECAES_GROUP - 1) / DECAES_GROUP;
   unsigned long long processed = 0;
+  long long v0 = 0;
+  int q = DECAES_GROUP;  // next voxel of the current group (DECAES_GROUP = group exhausted)
+  bool more_groups = true;
   while (true) {
-    unsigned long long gidx = 0;
-    if (lane == 0) gidx = atomicAdd(&P.counters[0], 1ull);
-    gidx = __shfl_sync(DECAES_FULL_MASK, gidx, 0);
-    if ((long long)gidx >= ngroups) break;
-    const long long v0 = (long long)gidx * DECAES_GROUP;
-    // stage the group's signals: lane -> (echo offset, voxel) so that each load instruction touches
-    // 8 full 32-byte sectors (4 consecutive voxels per echo)
-    {
-      const int q = lane & 3, eo = lane >> 2;
-      for (int e = eo; e < P.nTE; e += 8) {
-        long long v = v0 + q;
-        W.sig[q * P.nTE + e] = (v < P.nvox) ? __ldg(P.image + v + (long long)e * P.stride) : 0.0;
+    // ---- find this warp's next voxel above threshold (NaN-fill the skipped ones on the way) ----
+    bool have = false;
+    long long v = 0;
+    const double *signal = nullptr;
+    while (!have) {
+      if (q >= DECAES_GROUP) {
+        if (!more_groups) break;
+        unsigned long long gidx = 0;
+        if (lane == 0) gidx = atomicAdd(&P.counters[0], 1ull);
+        gidx = __shfl_sync(DECAES_FULL_MASK, gidx, 0);
+        if ((long long)gidx >= ngroups) {
+          more_groups = false;
+          break;
+        }
+        v0 = (long long)gidx * DECAES_GROUP;
+        // stage the group's signals: lane -> (echo offset, voxel) so that each load instruction
+        // touches 8 full 32-byte sectors (4 consecutive voxels per echo)
+        const int qq = lane & 3, eo = lane >> 2;
+        for (int e = eo; e < P.nTE; e += 8) {
+          long long vv = v0 + qq;
+          W.sig[qq * P.nTE + e] = (vv < P.nvox) ? __ldg(P.image + vv + (long long)e * P.stride) : 0.0;
+        }
+        __syncwarp();
+        q = 0;
       }
-    }
-    __syncwarp();
-    for (int q = 0; q < DECAES_GROUP; q++) {
-      const long long v = v0 + q;
-      if (v >= P.nvox) break;
-      const double *signal = W.sig + q * P.nTE;
+      v = v0 + q;
+      if (v >= P.nvox) {
+        q = DECAES_GROUP;
+        continue;
+      }
+      signal = W.sig + q * P.nTE;
+      q++;
       if (signal[0] > P.Threshold) {  // src/T2mapSEcorr.jl:177
-        W.process(v, signal);
-        processed++;
+        have = true;
       } else {
         // skipped voxel: outputs are NaN (the reference pre-fills NaN, src/T2mapSEcorr.jl:36-52)
         const double nanv = CUDART_NAN;
@@ -187,7 +210,15 @@ __global__ void __launch_bounds__(32) voxel_pipeline_kernel(const __grid_constan
           for (int k = lane; k < P.nTE * P.nT2; k += 32) P.decaybasis[v + (long long)k * P.stride] = nanv;
       }
     }
-    __syncwarp();
+    if (!__syncthreads_or(have)) break;  // every warp of the CTA is out of work
+    if (have) W.phase_flip_angle(v, signal);
+    __syncthreads();
+    if (have) W.phase_basis();
+    __syncthreads();
+    if (have) {
+      W.phase_solve_and_save();
+      processed++;
+    }
   }
   if (lane == 0) {
     if (processed) atomicAdd(&P.counters[1], processed);
@@ -453,7 +484,7 @@ static int ensure(double **p, size_t *cap, size_t need_doubles) {
 struct Plan {
   PipeParams P;
   SetupParams S;
-  int smem_bytes, grid;
+  int smem_bytes, grid, warps_per_cta, cta_smem;
 };
 
 // Build kernel parameters (everything except volume pointers) and make sure the device workspace fits.
@@ -512,16 +543,18 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if ((size_t)plan->smem_bytes > prop.sharedMemPerBlockOptin)
     return fail(DECAES_EUNSUPPORTED, "problem needs %d bytes of shared memory per warp (> %zu)", plan->smem_bytes,
                 prop.sharedMemPerBlockOptin);
-  int occ = 0;
-  if (P.gram) {
-    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, voxel_pipeline_kernel<true>, 32, plan->smem_bytes));
-  } else {
-    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, voxel_pipeline_kernel<false>, 32, plan->smem_bytes));
-  }
-  if (occ < 1) return fail(DECAES_ECUDA, "voxel_pipeline_kernel cannot be resident (occupancy 0)");
-  plan->grid = occ * prop.multiProcessorCount;
+  // one persistent CTA per SM; as many warps as shared memory allows (registers: launch bounds)
+  int wpc = (int)std::min<size_t>(DECAES_MAX_WARPS, (prop.sharedMemPerBlockOptin - 1024) / plan->smem_bytes);
+  if (const char *e = getenv("DECAES_WARPS_PER_CTA")) wpc = std::max(1, std::min(wpc, atoi(e)));
+  if (wpc < 1) return fail(DECAES_EUNSUPPORTED, "not enough shared memory for one warp");
+  P.warps_per_cta = wpc, P.smem_per_warp = plan->smem_bytes;
+  plan->warps_per_cta = wpc;
+  plan->cta_smem = wpc * plan->smem_bytes;
+  if (P.gram)
+    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
+  else
+    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
+  plan->grid = prop.multiProcessorCount;
 
   ScratchLayout sl(nTE, nT2, P.copy_elems, o->reg == DECAES_REG_GCV);
   P.scratch_per_warp = sl.total;
@@ -539,7 +572,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     CUDA_TRY(cudaMalloc(&ws.dbasis_cm, cm * sizeof(double)));
     ws.basis_cm_cap = cm;
   }
-  if ((rc = ensure(&ws.scratch, &ws.scratch_cap, (size_t)plan->grid * sl.total))) return rc;
+  if ((rc = ensure(&ws.scratch, &ws.scratch_cap, (size_t)plan->grid * wpc * sl.total))) return rc;
   if ((rc = ensure(&ws.gram_set, &ws.gram_cap, (size_t)nA * P.a_elems))) return rc;
   P.gram_set = ws.gram_set;
   if (!ws.counters) CUDA_TRY(cudaMalloc(&ws.counters, 8 * sizeof(unsigned long long)));
@@ -587,11 +620,11 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
   }
   CUDA_TRY(cudaEventRecord(ws.ev[1], stream));
   int64_t ngroups = (nvox + DECAES_GROUP - 1) / DECAES_GROUP;
-  int grid = (int)std::min<int64_t>(plan.grid, std::max<int64_t>(ngroups, 1));
+  int grid = (int)std::min<int64_t>(plan.grid, std::max<int64_t>((ngroups + plan.warps_per_cta - 1) / plan.warps_per_cta, 1));
   if (P.gram)
-    voxel_pipeline_kernel<true><<<grid, 32, plan.smem_bytes, stream>>>(P);
+    voxel_pipeline_kernel<true><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
   else
-    voxel_pipeline_kernel<false><<<grid, 32, plan.smem_bytes, stream>>>(P);
+    voxel_pipeline_kernel<false><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(ws.ev[2], stream));
   ws.ev_pending = true;

@@ -75,21 +75,20 @@ __device__ __noinline__ bool gram_append(const GramProb &p, const GramWs &ws, in
   const int lane = lane_id();
   double *T = p.T;
   const int ld = p.ld;
-  for (int t = lane; t < k; t += 32) ws.t1[t] = gram_G(p, ws.P[t], j);
+  _Pragma("unroll 1") for (int t = lane; t < k; t += 32) ws.t1[t] = gram_G(p, ws.P[t], j);
   __syncwarp();
   // l = M g  (lane <-> row t; for fixed u the lanes read consecutive words)
   double ll = 0.0, ly = 0.0;
-  for (int t = lane; t < k; t += 32) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
+    double a0 = 0.0, a1 = 0.0;
     int u = 0;
-    for (; u + 3 <= t; u += 4) {
+#pragma unroll 1
+    for (; u + 1 <= t; u += 2) {
       a0 = fma(GM_(t, u), ws.t1[u], a0);
       a1 = fma(GM_(t, u + 1), ws.t1[u + 1], a1);
-      a2 = fma(GM_(t, u + 2), ws.t1[u + 2], a2);
-      a3 = fma(GM_(t, u + 3), ws.t1[u + 3], a3);
     }
-    for (; u <= t; u++) a0 = fma(GM_(t, u), ws.t1[u], a0);
-    double lt = (a0 + a1) + (a2 + a3);
+    if (u <= t) a0 = fma(GM_(t, u), ws.t1[u], a0);
+    double lt = a0 + a1;
     ws.t2[t] = lt;
     ll = fma(lt, lt, ll);
     ly = fma(lt, ws.y[t], ly);
@@ -97,22 +96,21 @@ __device__ __noinline__ bool gram_append(const GramProb &p, const GramWs &ws, in
   ll = warp_sum(ll), ly = warp_sum(ly);
   const double d2 = (T[j * ld + j] + p.mu2) - ll;
   if (!(d2 > 0.0)) return false;
-  const double dinv = rsqrt(d2);
+  const double dinv = drsqrt(d2);
   const double ynew = (p.c[j] - ly) * dinv;
   if (need_positive && !(ynew > 0.0)) return false;
   __syncwarp();
   // new row of M: M(k,u) = -dinv * sum_{t >= u} l_t M(t,u)   (lane <-> column u, own row contiguous in t)
-  for (int u = lane; u < k; u += 32) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  _Pragma("unroll 1") for (int u = lane; u < k; u += 32) {
+    double a0 = 0.0, a1 = 0.0;
     int t = u;
-    for (; t + 3 < k; t += 4) {
+#pragma unroll 1
+    for (; t + 1 < k; t += 2) {
       a0 = fma(ws.t2[t], GM_(t, u), a0);
       a1 = fma(ws.t2[t + 1], GM_(t + 1, u), a1);
-      a2 = fma(ws.t2[t + 2], GM_(t + 2, u), a2);
-      a3 = fma(ws.t2[t + 3], GM_(t + 3, u), a3);
     }
-    for (; t < k; t++) a0 = fma(ws.t2[t], GM_(t, u), a0);
-    double mu_ = -dinv * ((a0 + a1) + (a2 + a3));
+    if (t < k) a0 = fma(ws.t2[t], GM_(t, u), a0);
+    double mu_ = -dinv * (a0 + a1);
     GM_(k, u) = mu_;
     ws.s[u] = fma(ynew, mu_, ws.s[u]);
   }
@@ -133,7 +131,7 @@ __device__ __noinline__ void gram_rebuild(const GramProb &p, const GramWs &ws, i
   const int kold = k, ld = p.ld;
   double *T = p.T;
   // s = M[0:from]' y[0:from]
-  for (int u = lane; u < kold; u += 32) {
+  _Pragma("unroll 1") for (int u = lane; u < kold; u += 32) {
     double a = 0.0;
     for (int t = u; t < from; t++) a = fma(GM_(t, u), ws.y[t], a);
     ws.s[u] = a;
@@ -154,17 +152,16 @@ __device__ __noinline__ void gram_rebuild(const GramProb &p, const GramWs &ws, i
 // w_j = c_j - sum_t G(P[t], j) * s_t for every column; entries of active columns are forced to 0.
 __device__ __noinline__ void gram_dual(const GramProb &p, const GramWs &ws, int k, unsigned long long mask) {
   const int lane = lane_id();
-  for (int j = lane; j < p.n; j += 32) {
-    double a0 = p.c[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  _Pragma("unroll 1") for (int j = lane; j < p.n; j += 32) {
+    double a0 = p.c[j], a1 = 0.0;
     int t = 0;
-    for (; t + 3 < k; t += 4) {
+#pragma unroll 1
+    for (; t + 1 < k; t += 2) {
       a0 = fma(-gram_G(p, ws.P[t], j), ws.s[t], a0);
       a1 = fma(-gram_G(p, ws.P[t + 1], j), ws.s[t + 1], a1);
-      a2 = fma(-gram_G(p, ws.P[t + 2], j), ws.s[t + 2], a2);
-      a3 = fma(-gram_G(p, ws.P[t + 3], j), ws.s[t + 3], a3);
     }
-    for (; t < k; t++) a0 = fma(-gram_G(p, ws.P[t], j), ws.s[t], a0);
-    ws.w[j] = ((mask >> j) & 1ull) ? 0.0 : (a0 + a1) + (a2 + a3);
+    if (t < k) a0 = fma(-gram_G(p, ws.P[t], j), ws.s[t], a0);
+    ws.w[j] = ((mask >> j) & 1ull) ? 0.0 : a0 + a1;
   }
   __syncwarp();
 }
@@ -181,9 +178,9 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
   if (!warm) {
     mask = 0ull;
     // dual as if the last column were active; w[n-1] = 0, or 1 if every other dual is <= 0
-    const double xj = p.c[n - 1] / (p.T[(n - 1) * p.ld + (n - 1)] + p.mu2);
+    const double xj = ddiv(p.c[n - 1], p.T[(n - 1) * p.ld + (n - 1)] + p.mu2);
     bool anypos = false;
-    for (int j = lane; j < n; j += 32) {
+    _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
       double wj = (j < n - 1) ? fma(-gram_G(p, n - 1, j), xj, p.c[j]) : 0.0;
       ws.w[j] = wj;
       ws.x[j] = 0.0;
@@ -201,7 +198,7 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
       if (lane == 0) ws.P[kk] = j;
       kk++;
     }
-    for (int j = lane; j < n; j += 32)
+    _Pragma("unroll 1") for (int j = lane; j < n; j += 32)
       if (!((mask >> j) & 1ull)) ws.x[j] = 0.0;
     __syncwarp();
     k = kk;
@@ -209,7 +206,7 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
     if (k != kk) mask = mask_of(ws.P, k);  // a column was dropped as dependent
     need_solve_check = (k > 0);
     if (k == 0) {
-      for (int j = lane; j < n; j += 32) ws.w[j] = p.c[j];
+      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) ws.w[j] = p.c[j];
       __syncwarp();
     }
   }
@@ -223,7 +220,7 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
       while (true) {
         double best = 0.0;
         int bj = 0x7fffffff;
-        for (int j = lane; j < n; j += 32) {
+        _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
           double v = ws.w[j];
           if (!((mask >> j) & 1ull) && v > best) best = v, bj = j;
         }
@@ -253,17 +250,17 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
       }
       double al = 2.0;
       int imv = 0x7fffffff;
-      for (int t = lane; t < k; t += 32) {
+      _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
         double st = ws.s[t];
         if (st <= 0.0) {
           double xi = ws.x[ws.P[t]];
-          double tt = -xi / (st - xi);
+          double tt = ddiv(-xi, st - xi);
           if (al > tt) al = tt, imv = t;
         }
       }
       warp_argmin_first(al, imv);
       if (!(al < 2.0)) break;  // all coefficients feasible
-      for (int t = lane; t < k; t += 32) {
+      _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
         int jx = ws.P[t];
         ws.x[jx] = fma(al, ws.s[t] - ws.x[jx], ws.x[jx]);
       }
@@ -290,7 +287,7 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
     }
     if (terminated) break;
 
-    for (int t = lane; t < k; t += 32) ws.x[ws.P[t]] = ws.s[t];
+    _Pragma("unroll 1") for (int t = lane; t < k; t += 32) ws.x[ws.P[t]] = ws.s[t];
     __syncwarp();
     gram_dual(p, ws, k, mask);
   }
@@ -299,7 +296,7 @@ __device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, b
   o.k = k;
   o.mask = mask;
   double acc = 0.0;
-  for (int j = lane; j < n; j += 32) acc = fma(ws.x[j], ws.x[j], acc);
+  _Pragma("unroll 1") for (int j = lane; j < n; j += 32) acc = fma(ws.x[j], ws.x[j], acc);
   o.xnorm_sq = warp_sum(acc);
   return o;
 }

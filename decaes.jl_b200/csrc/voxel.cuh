@@ -36,6 +36,7 @@ struct PipeParams {
   const double *dbasis_cm;  // [nA][nT2][nTE]   d/d(alpha in degrees)
   const double *gram_set;   // [nA][nT2*ldg]     A_k'A_k per grid angle (Gram solver)
   int gram, ldg;            // solver variant (1 = normal-equation active set), leading dimension of G
+  int warps_per_cta, smem_per_warp;  // CTA shape: bytes of dynamic shared memory owned by each warp
   double angles[DECAES_MAX_ANGLES];                            // flip-angle grid (degrees)
   double logT2[DECAES_MAX_NT2], E2[DECAES_MAX_NT2];            // log(T2_j), exp(-(TE/2)/T2_j)
   double weights[DECAES_MAX_NT2];                              // sigmoid weights (has_sigmoid)
@@ -461,7 +462,7 @@ struct Warp {
   }
   static __device__ __forceinline__ double norm2(double ax, double ay, double bx, double by) {
     double dx = ax - bx, dy = ay - by;
-    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    return dsqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
   }
   static __device__ double menger(double jx, double jy, double kx, double ky, double lx, double ly) {
     double jk0 = jx - kx, jk1 = jy - ky, kl0 = kx - lx, kl1 = ky - ly, lj0 = lx - jx, lj1 = ly - jy;
@@ -469,7 +470,7 @@ struct Warp {
     double d2 = __dadd_rn(__dmul_rn(kl0, kl0), __dmul_rn(kl1, kl1));
     double d3 = __dadd_rn(__dmul_rn(lj0, lj0), __dmul_rn(lj1, lj1));
     double cr = __dsub_rn(__dmul_rn(jk0, kl1), __dmul_rn(jk1, kl0));
-    return __dmul_rn(2.0, cr) / sqrt(__dmul_rn(__dmul_rn(d1, d2), d3));
+    return ddiv(__dmul_rn(2.0, cr), dsqrt(__dmul_rn(__dmul_rn(d1, d2), d3)));
   }
 
   // cached evaluation of P(t) = (log ||Ax-b||^2, log ||x||^2); returns the point-cache index
@@ -477,8 +478,8 @@ struct Warp {
     double *pts = g + sl.lc_pts;
     for (int i = 0; i < npts; i++)
       if (isapprox(t, pts[4 * i])) return i;
-    cache_solve(exp(t), Asrc);
-    double xi = log(cur_resnorm_sq()), eta = log(cur_seminorm_sq());
+    cache_solve(dexp(t), Asrc);
+    double xi = dlog(cur_resnorm_sq()), eta = dlog(cur_seminorm_sq());
     int i = npts;
     if (npts < DECAES_LC_MAX) {
       if (lane == 0) pts[4 * i] = t, pts[4 * i + 1] = xi, pts[4 * i + 2] = eta, pts[4 * i + 3] = -CUDART_INF;
@@ -818,10 +819,10 @@ struct Warp {
   // c = A' bd  (lane <-> column, coalesced rows of the row-major matrix)
   __device__ __noinline__ void gram_rhs(const double *Arm) {
     const int nTE = P.nTE, ld = P.ld;
-    for (int j = lane; j < P.nT2; j += 32) {
+    _Pragma("unroll 1") for (int j = lane; j < P.nT2; j += 32) {
       double a0 = 0.0, a1 = 0.0;
       int i = 0;
-      for (; i + 1 < nTE; i += 2) {
+      _Pragma("unroll 1") for (; i + 1 < nTE; i += 2) {
         a0 = fma(Arm[i * ld + j], bd[i], a0);
         a1 = fma(Arm[(i + 1) * ld + j], bd[i + 1], a1);
       }
@@ -835,10 +836,10 @@ struct Warp {
   __device__ __noinline__ double gram_residual(const double *Acm, int k) {
     const int nTE = P.nTE;
     double acc = 0.0;
-    for (int i = lane; i < nTE; i += 32) {
+    _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
       double a0 = bd[i], a1 = 0.0;
       int t = 0;
-      for (; t + 1 < k; t += 2) {
+      _Pragma("unroll 1") for (; t + 1 < k; t += 2) {
         a0 = fma(-Acm[gws.P[t] * nTE + i], gws.s[t], a0);
         a1 = fma(-Acm[gws.P[t + 1] * nTE + i], gws.s[t + 1], a1);
       }
@@ -859,11 +860,11 @@ struct Warp {
     double *T = Gs;
     const int ld = P.ldg;
     // g_t = A[:,P[t]]' r - mu2 s_t      (lane <-> active column)
-    for (int t = lane; t < k; t += 32) {
+    _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
       const double *col = Acm + gws.P[t] * nTE;
       double a0 = 0.0, a1 = 0.0;
       int i = 0;
-      for (; i + 1 < nTE; i += 2) {
+      _Pragma("unroll 1") for (; i + 1 < nTE; i += 2) {
         a0 = fma(col[i], fit[i], a0);
         a1 = fma(col[i + 1], fit[i + 1], a1);
       }
@@ -872,14 +873,14 @@ struct Warp {
     }
     __syncwarp();
     // v = M g
-    for (int t = lane; t < k; t += 32) {
+    _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
       double a = 0.0;
       for (int u = 0; u <= t; u++) a = fma(GM_(t, u), gws.t1[u], a);
       gws.t2[t] = a;
     }
     __syncwarp();
     // s += M' v
-    for (int u = lane; u < k; u += 32) {
+    _Pragma("unroll 1") for (int u = lane; u < k; u += 32) {
       double a = 0.0;
       for (int t = u; t < k; t++) a = fma(GM_(t, u), gws.t2[t], a);
       double sn = gws.s[u] + a;
@@ -917,7 +918,7 @@ struct Warp {
     u = gram_solve_unreg(src, o);
     const double *dAk = P.dbasis_cm + (size_t)kang * nTE * n;
     double acc = 0.0;
-    for (int i = lane; i < nTE; i += 32) {
+    _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
       double dax = 0.0;
       for (int t = 0; t < o.k; t++)
         if (gws.s[t] > 0.0) dax = fma(gws.s[t], dAk[gws.P[t] * nTE + i], dax);
@@ -1003,7 +1004,7 @@ struct Warp {
     }
     __syncwarp();
     if (P.decaybasis && !P.fixed_alpha) {
-      for (int k = lane; k < ETL * n; k += 32) P.decaybasis[v + (long long)k * P.stride] = pcm[k];
+      _Pragma("unroll 1") for (int k = lane; k < ETL * n; k += 32) P.decaybasis[v + (long long)k * P.stride] = pcm[k];
     }
   }
 
@@ -1045,7 +1046,7 @@ struct Warp {
         hit = i;
         break;
       } else {
-        double dd = mu > mui ? mu / mui : mui / mu;  // monotone in |log mu - log mui|
+        double dd = mu > mui ? ddiv(mu, mui) : ddiv(mui, mu);  // monotone in |log mu - log mui|
         if (dd < dbest && slot_mask[i] != 0ull) dbest = dd, nearest = i;
       }
     }
@@ -1059,7 +1060,7 @@ struct Warp {
     GramOut o;
     if (nearest >= 0) {
       const double *sx = g + sl.slots_x + nearest * n;
-      for (int j = lane; j < n; j += 32) gws.x[j] = sx[j];
+      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = sx[j];
       __syncwarp();
       o = gram_nnls(pr, gws, true, slot_mask[nearest]);
     } else {
@@ -1067,45 +1068,56 @@ struct Warp {
     }
     double r2 = gram_residual(src.Acm, o.k);
     double *sx = g + sl.slots_x + cur_slot * n;
-    for (int j = lane; j < n; j += 32) sx[j] = gws.x[j];
+    _Pragma("unroll 1") for (int j = lane; j < n; j += 32) sx[j] = gws.x[j];
     if (lane == 0)
       slot_mu[cur_slot] = mu, slot_r2[cur_slot] = r2, slot_x2[cur_slot] = o.xnorm_sq, slot_mask[cur_slot] = o.mask;
     __syncwarp();
   }
 
   // ================= one voxel =================
-  __device__ __noinline__ void process(long long v, const double *signal /* smem, nTE */) {
-    const int nTE = P.nTE, n = P.nT2;
-    // normalise  src/T2mapSEcorr.jl:205-218
+  // The per-voxel chain is split into three phases so that the warps of a CTA can be kept in the
+  // same phase (CTA barriers in the kernel): the pipeline is instruction-cache bound and warps that
+  // run the same code at the same time share its lines.
+  long long v_cur;
+  double max_signal_cur, alpha_cur;
+
+  // phase 1: normalise (src/T2mapSEcorr.jl:205-218) and fit the flip angle (:409-423)
+  __device__ __noinline__ void phase_flip_angle(long long v, const double *signal /* smem, nTE */) {
+    const int nTE = P.nTE;
+    v_cur = v;
     double mx = 0.0;
     for (int i = lane; i < nTE; i += 32) {
       double bi = signal[i];
       mx = bi > mx ? bi : mx;
     }
     const double max_signal = warp_max(mx);
+    max_signal_cur = max_signal;
     for (int i = lane; i < nTE; i += 32) bd[i] = (max_signal > 0) ? signal[i] / max_signal : signal[i];
     __syncwarp();
+    if (P.alpha_provided) alpha_cur = P.alpha[v];
+    else if (P.fixed_alpha) alpha_cur = P.SetFlipAngle;
+    else alpha_cur = optimize_flip_angle();
+  }
 
-    // flip angle + basis
-    double alpha;
-    const double *Asrc;
-    if (P.alpha_provided) {
-      alpha = P.alpha[v];
-      basis_at(alpha, v);
-      Asrc = g + sl.pristine;
-    } else if (P.fixed_alpha) {
-      alpha = P.SetFlipAngle;
-      Asrc = P.basis_rm;
+  // phase 2: EPG basis at the fitted angle (+ Gram matrix / right-hand side)
+  __device__ __noinline__ void phase_basis() {
+    if (P.fixed_alpha && !P.alpha_provided) {
       if constexpr (GRAM) {
         cursrc.G = P.gram_set, cursrc.ldg = P.ldg, cursrc.Arm = P.basis_rm, cursrc.Acm = P.basis_cm;
         stage_bulk(Gs, P.gram_set, (unsigned)(P.a_elems * 8));
         gram_rhs(cursrc.Arm);
       }
     } else {
-      alpha = optimize_flip_angle();
-      basis_at(alpha, v);
-      Asrc = g + sl.pristine;
+      basis_at(alpha_cur, v_cur);
     }
+  }
+
+  // phase 3: regularised NNLS, output maps, T2part epilogue
+  __device__ __noinline__ void phase_solve_and_save() {
+    const int nTE = P.nTE, n = P.nT2;
+    const long long v = v_cur;
+    const double max_signal = max_signal_cur, alpha = alpha_cur;
+    const double *Asrc = (P.fixed_alpha && !P.alpha_provided) ? P.basis_rm : g + sl.pristine;
 
     // T2_distribution!  src/T2mapSEcorr.jl:475-505
     double mu = CUDART_NAN, chi2 = CUDART_NAN;
@@ -1119,7 +1131,7 @@ struct Warp {
       case 1: {  // lsqnonneg_lcurve!  src/lsqnonneg.jl:812-840
         cache_reset();
         double logmu = lcurve_corner(Asrc);
-        mu = exp(logmu);
+        mu = dexp(logmu);
         cache_solve(mu, Asrc);
         src_kind = 1;
         if (want_chi2) {  // the unregularised solve only feeds chi2factor
