@@ -506,6 +506,10 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   // solver variant: normal-equation active set (default) or the QR port (DECAES_SOLVER=qr, kept for A/B checks)
   const char *sv = getenv("DECAES_SOLVER");
   P.gram = !(sv && strcmp(sv, "qr") == 0);
+  // Brent-based choosers (gcv / chi2 / mdp) are numerically stable searches: keep their inputs at
+  // reference-level accuracy.  The L-curve search flips on 1-ulp noise anyway (tests/test_oracle_sensitivity.py).
+  P.refine_tikh = (o->reg != DECAES_REG_LCURVE);
+  if (const char *e = getenv("DECAES_REFINE")) P.refine_tikh = atoi(e);
   P.ldg = (nT2 + 1) | 1;  // one array holds the lower triangle of G and, above it, M = L^-1 (gram.cuh)
   if (P.gram) P.a_elems = nT2 * P.ldg;
   P.a_elems = (P.a_elems + 1) & ~1;

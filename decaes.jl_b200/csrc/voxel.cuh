@@ -37,6 +37,7 @@ struct PipeParams {
   const double *gram_set;   // [nA][nT2*ldg]     A_k'A_k per grid angle (Gram solver)
   int gram, ldg;            // solver variant (1 = normal-equation active set), leading dimension of G
   int warps_per_cta, smem_per_warp;  // CTA shape: bytes of dynamic shared memory owned by each warp
+  int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
   double angles[DECAES_MAX_ANGLES];                            // flip-angle grid (degrees)
   double logT2[DECAES_MAX_NT2], E2[DECAES_MAX_NT2];            // log(T2_j), exp(-(TE/2)/T2_j)
   double weights[DECAES_MAX_NT2];                              // sigmoid weights (has_sigmoid)
@@ -473,14 +474,34 @@ struct Warp {
     return ddiv(__dmul_rn(2.0, cr), dsqrt(__dmul_rn(__dmul_rn(d1, d2), d3)));
   }
 
+  // The L-curve bookkeeping scans (point cache, state cache) are lane-parallel: lane <-> cache entry,
+  // with warp reductions that reproduce the sequential "first match / first maximum" semantics.
+
+  // first index i with isapprox(t, key_i), or INT_MAX
+  __device__ __noinline__ int lc_find(double t, int npts) {
+    const double *pts = g + sl.lc_pts;
+    int found = 0x7fffffff;
+    for (int i = lane; i < npts; i += 32)
+      if (isapprox(t, pts[4 * i])) {
+        found = i;
+        break;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      int other = __shfl_xor_sync(DECAES_FULL_MASK, found, o);
+      found = other < found ? other : found;
+    }
+    return found;
+  }
+
   // cached evaluation of P(t) = (log ||Ax-b||^2, log ||x||^2); returns the point-cache index
   __device__ __noinline__ int lc_eval(double t, int &npts, const double *Asrc) {
     double *pts = g + sl.lc_pts;
-    for (int i = 0; i < npts; i++)
-      if (isapprox(t, pts[4 * i])) return i;
+    int i = lc_find(t, npts);
+    if (i != 0x7fffffff) return i;
     cache_solve(dexp(t), Asrc);
     double xi = dlog(cur_resnorm_sq()), eta = dlog(cur_seminorm_sq());
-    int i = npts;
+    i = npts;
     if (npts < DECAES_LC_MAX) {
       if (lane == 0) pts[4 * i] = t, pts[4 * i + 1] = xi, pts[4 * i + 2] = eta, pts[4 * i + 3] = -CUDART_INF;
       npts++;
@@ -500,12 +521,19 @@ struct Warp {
       double x = sx[q], px = pts[4 * pi + 1], py = pts[4 * pi + 2];
       double C = -CUDART_INF;
       if (fmin(norm2(px, py, tlx, tly), norm2(px, py, brx, bry)) > Ctol) {
-        double xm = -CUDART_INF, xp = CUDART_INF, mx = px, my = py, qx = px, qy = py;
-        for (int k = 0; k < npts; k++) {
+        // nearest cached abscissae on either side of x (src/lsqnonneg.jl:954-959)
+        double xm = -CUDART_INF, xp = CUDART_INF;
+        int im = 0x7fffffff, ip = 0x7fffffff;
+        for (int k = lane; k < npts; k += 32) {
           double _x = pts[4 * k];
-          if (xm < _x && _x < x) xm = _x, mx = pts[4 * k + 1], my = pts[4 * k + 2];
-          if (x < _x && _x < xp) xp = _x, qx = pts[4 * k + 1], qy = pts[4 * k + 2];
+          if (xm < _x && _x < x) xm = _x, im = k;
+          if (x < _x && _x < xp) xp = _x, ip = k;
         }
+        warp_argmax_first(xm, im);
+        warp_argmin_first(xp, ip);
+        double mx = px, my = py, qx = px, qy = py;
+        if (im != 0x7fffffff) mx = pts[4 * im + 1], my = pts[4 * im + 2];
+        if (ip != 0x7fffffff) qx = pts[4 * ip + 1], qy = pts[4 * ip + 2];
         C = menger(mx, my, px, py, qx, qy);
       }
       __syncwarp();
@@ -514,12 +542,49 @@ struct Warp {
     }
   }
 
-  __device__ int lc_argmax(int npts) {
+  // mapfindmax over the curvatures: first maximum under Base.isless (NaN is maximal)
+  __device__ __noinline__ int lc_argmax(int npts) {
     const double *pts = g + sl.lc_pts;
-    int best = 0;
-    for (int i = 1; i < npts; i++)
-      if (isless_f(pts[4 * best + 3], pts[4 * i + 3])) best = i;
-    return best;
+    int bi = 0x7fffffff;
+    double bc = 0.0;
+    for (int i = lane; i < npts; i += 32) {
+      double c = pts[4 * i + 3];
+      if (bi == 0x7fffffff || isless_f(bc, c)) bc = c, bi = i;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double oc = __shfl_xor_sync(DECAES_FULL_MASK, bc, o);
+      int oi = __shfl_xor_sync(DECAES_FULL_MASK, bi, o);
+      bool take = (oi != 0x7fffffff) &&
+                  (bi == 0x7fffffff || isless_f(bc, oc) || (!isless_f(oc, bc) && oi < bi));
+      if (take) bc = oc, bi = oi;
+    }
+    return __shfl_sync(DECAES_FULL_MASK, bi, 0);
+  }
+
+  // backtracking (src/lsqnonneg.jl:892-900): among the stored states that have the arg-max point as
+  // an interior point, the sequential scan ends on the LAST one of minimal width, provided that width
+  // does not exceed the current state's.  Returns its index or -1.
+  __device__ __noinline__ int lc_backtrack(double xb, double wcur, int nst) {
+    const double *sts = g + sl.lc_states;
+    double bw = CUDART_INF;
+    int bk = -1;
+    for (int k = lane; k < nst; k += 32) {
+      const double *s = sts + 6 * k;
+      if (s[1] == xb || s[2] == xb) {
+        double w = fabs(s[3] - s[0]);
+        if (w <= bw) bw = w, bk = k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ow = __shfl_xor_sync(DECAES_FULL_MASK, bw, o);
+      int ok = __shfl_xor_sync(DECAES_FULL_MASK, bk, o);
+      if (ok >= 0 && (bk < 0 || ow < bw || (ow == bw && ok > bk))) bw = ow, bk = ok;
+    }
+    bk = __shfl_sync(DECAES_FULL_MASK, bk, 0);
+    bw = __shfl_sync(DECAES_FULL_MASK, bw, 0);
+    return (bk >= 0 && bw <= wcur) ? bk : -1;
   }
 
   __device__ __noinline__ double lcurve_corner(const double *Asrc) {
@@ -541,12 +606,11 @@ struct Warp {
       iter++;
       {  // backtracking  :892-900
         double xb = pts[4 * lc_argmax(npts)];
-        for (int k = 0; k < nst; k++) {
-          const double *s = sts + 6 * k;
-          if ((s[1] == xb || s[2] == xb) && fabs(s[3] - s[0]) <= fabs(sx[3] - sx[0])) {
-            unsigned long long packed = (unsigned long long)__double_as_longlong(s[4]);
-            for (int q = 0; q < 4; q++) sx[q] = s[q], si[q] = (int)((packed >> (16 * q)) & 0xffff);
-          }
+        int kb = lc_backtrack(xb, fabs(sx[3] - sx[0]), nst);
+        if (kb >= 0) {
+          const double *s = sts + 6 * kb;
+          unsigned long long packed = (unsigned long long)__double_as_longlong(s[4]);
+          for (int q = 0; q < 4; q++) sx[q] = s[q], si[q] = (int)((packed >> (16 * q)) & 0xffff);
         }
       }
       double C2 = pts[4 * si[1] + 3], C3 = pts[4 * si[2] + 3];
@@ -820,14 +884,18 @@ struct Warp {
   __device__ __noinline__ void gram_rhs(const double *Arm) {
     const int nTE = P.nTE, ld = P.ld;
     _Pragma("unroll 1") for (int j = lane; j < P.nT2; j += 32) {
-      double a0 = 0.0, a1 = 0.0;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      const double *col = Arm + j;
       int i = 0;
-      _Pragma("unroll 1") for (; i + 1 < nTE; i += 2) {
-        a0 = fma(Arm[i * ld + j], bd[i], a0);
-        a1 = fma(Arm[(i + 1) * ld + j], bd[i + 1], a1);
+      // eight independent global loads in flight per lane (the matrix lives in L2)
+      _Pragma("unroll 1") for (; i + 7 < nTE; i += 8) {
+        double v0 = col[i * ld], v1 = col[(i + 1) * ld], v2 = col[(i + 2) * ld], v3 = col[(i + 3) * ld];
+        double v4 = col[(i + 4) * ld], v5 = col[(i + 5) * ld], v6 = col[(i + 6) * ld], v7 = col[(i + 7) * ld];
+        a0 = fma(v0, bd[i], a0), a1 = fma(v1, bd[i + 1], a1), a2 = fma(v2, bd[i + 2], a2), a3 = fma(v3, bd[i + 3], a3);
+        a0 = fma(v4, bd[i + 4], a0), a1 = fma(v5, bd[i + 5], a1), a2 = fma(v6, bd[i + 6], a2), a3 = fma(v7, bd[i + 7], a3);
       }
-      if (i < nTE) a0 = fma(Arm[i * ld + j], bd[i], a0);
-      cvec[j] = a0 + a1;
+      _Pragma("unroll 1") for (; i < nTE; i++) a0 = fma(col[i * ld], bd[i], a0);
+      cvec[j] = (a0 + a1) + (a2 + a3);
     }
     __syncwarp();
   }
@@ -837,14 +905,16 @@ struct Warp {
     const int nTE = P.nTE;
     double acc = 0.0;
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
-      double a0 = bd[i], a1 = 0.0;
+      double a0 = bd[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
       int t = 0;
-      _Pragma("unroll 1") for (; t + 1 < k; t += 2) {
-        a0 = fma(-Acm[gws.P[t] * nTE + i], gws.s[t], a0);
-        a1 = fma(-Acm[gws.P[t + 1] * nTE + i], gws.s[t + 1], a1);
+      _Pragma("unroll 1") for (; t + 3 < k; t += 4) {
+        double v0 = Acm[gws.P[t] * nTE + i], v1 = Acm[gws.P[t + 1] * nTE + i];
+        double v2 = Acm[gws.P[t + 2] * nTE + i], v3 = Acm[gws.P[t + 3] * nTE + i];
+        a0 = fma(-v0, gws.s[t], a0), a1 = fma(-v1, gws.s[t + 1], a1);
+        a2 = fma(-v2, gws.s[t + 2], a2), a3 = fma(-v3, gws.s[t + 3], a3);
       }
-      if (t < k) a0 = fma(-Acm[gws.P[t] * nTE + i], gws.s[t], a0);
-      double r = a0 + a1;
+      _Pragma("unroll 1") for (; t < k; t++) a0 = fma(-Acm[gws.P[t] * nTE + i], gws.s[t], a0);
+      double r = (a0 + a1) + (a2 + a3);
       fit[i] = r;
       acc = fma(r, r, acc);
     }
@@ -1067,6 +1137,15 @@ struct Warp {
       o = gram_nnls(pr, gws, false, 0ull);
     }
     double r2 = gram_residual(src.Acm, o.k);
+    if (o.k > 0 && P.refine_tikh) {
+      // one refinement step on the explicit residual: x(mu) accurate to ~cond([A; mu I]) * eps, so
+      // that ||Ax - b||^2 and ||x||^2 (the inputs of the mu searches) carry reference-level noise
+      gram_refine(src.Acm, o.k, pr.mu2);
+      r2 = gram_residual(src.Acm, o.k);
+      double acc = 0.0;
+      for (int t = lane; t < o.k; t += 32) acc = fma(gws.s[t], gws.s[t], acc);
+      o.xnorm_sq = warp_sum(acc);
+    }
     double *sx = g + sl.slots_x + cur_slot * n;
     _Pragma("unroll 1") for (int j = lane; j < n; j += 32) sx[j] = gws.x[j];
     if (lane == 0)
