@@ -9,7 +9,7 @@
 #define DECAES_FULL_MASK 0xffffffffu
 #define DECAES_MAX_ANGLES 64   // flip-angle grid is tracked in one 64-bit mask
 #define DECAES_MAX_NT2 64      // per-column flags live in one 64-bit mask
-#define DECAES_LC_MAX 96       // L-curve point / state cache capacity per voxel
+#define DECAES_LC_MAX 64       // L-curve point / state cache capacity per voxel
 #define DECAES_NCACHE 8        // NNLSTikhonovRegProblemCache slots (src/lsqnonneg.jl:396)
 #define DECAES_GROUP 4         // voxels fetched per work item = one 32-byte sector per echo
 #define DECAES_MAX_WARPS 12    // warps per persistent CTA (register file: 65536 / (12*32) = 170 regs/thread)
@@ -27,12 +27,12 @@ __device__ __noinline__ double dlog(double a) { return log(a); }
 __device__ __noinline__ double dexp(double a) { return exp(a); }
 
 // Butterfly sums: every lane ends with the bitwise-identical total (addition commutes).
-__device__ __noinline__ double warp_sum(double v) {
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DECAES_FULL_MASK, v, o);
   return v;
 }
-__device__ __noinline__ double warp_max(double v) {
+__device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(DECAES_FULL_MASK, v, o));
   return v;

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
 
   const long long ngroups = (P.nvox + DECAES_GROUP - 1) / DECAES_GROUP;
   unsigned long long processed = 0;
+  long long cyc[4] = {0, 0, 0, 0};  // per-warp cycles: barrier wait, flip angle, basis, solve+save
   long long v0 = 0;
   int q = DECAES_GROUP;  // next voxel of the current group (DECAES_GROUP = group exhausted)
   bool more_groups = true;
@@ -210,15 +211,29 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
           for (int k = lane; k < P.nTE * P.nT2; k += 32) P.decaybasis[v + (long long)k * P.stride] = nanv;
       }
     }
+    long long t0 = clock64();
     if (!__syncthreads_or(have)) break;  // every warp of the CTA is out of work
+    long long t1 = clock64();
     if (have) W.phase_flip_angle(v, signal);
-    __syncthreads();
+    long long t2 = clock64();
+    if (P.sync_mask & 1) __syncthreads();
+    long long t3 = clock64();
     if (have) W.phase_basis();
-    __syncthreads();
+    long long t4 = clock64();
+    if (P.sync_mask & 2) __syncthreads();
+    long long t5 = clock64();
     if (have) {
       W.phase_solve_and_save();
       processed++;
     }
+    long long t6 = clock64();
+    cyc[0] += (t1 - t0) + (t3 - t2) + (t5 - t4), cyc[1] += t2 - t1, cyc[2] += t4 - t3, cyc[3] += t6 - t5;
+  }
+  if (lane == 0) {
+    for (int c = 0; c < 4; c++) atomicAdd(&P.counters[4 + c], (unsigned long long)cyc[c]);
+#ifdef DECAES_PROFILE
+    for (int c = 0; c < PF_COUNT; c++) atomicAdd(&P.counters[8 + c], (unsigned long long)W.prof_cyc[c]);
+#endif
   }
   if (lane == 0) {
     if (processed) atomicAdd(&P.counters[1], processed);
@@ -510,6 +525,10 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   // reference-level accuracy.  The L-curve search flips on 1-ulp noise anyway (tests/test_oracle_sensitivity.py).
   P.refine_tikh = (o->reg != DECAES_REG_LCURVE);
   if (const char *e = getenv("DECAES_REFINE")) P.refine_tikh = atoi(e);
+  P.sync_mask = 3;
+  P.fa_warm = 1;
+  if (const char *e = getenv("DECAES_FA_WARM")) P.fa_warm = atoi(e);
+  if (const char *e = getenv("DECAES_SYNC_MASK")) P.sync_mask = atoi(e);
   P.ldg = (nT2 + 1) | 1;  // one array holds the lower triangle of G and, above it, M = L^-1 (gram.cuh)
   if (P.gram) P.a_elems = nT2 * P.ldg;
   P.a_elems = (P.a_elems + 1) & ~1;
@@ -579,7 +598,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if ((rc = ensure(&ws.scratch, &ws.scratch_cap, (size_t)plan->grid * wpc * sl.total))) return rc;
   if ((rc = ensure(&ws.gram_set, &ws.gram_cap, (size_t)nA * P.a_elems))) return rc;
   P.gram_set = ws.gram_set;
-  if (!ws.counters) CUDA_TRY(cudaMalloc(&ws.counters, 8 * sizeof(unsigned long long)));
+  if (!ws.counters) CUDA_TRY(cudaMalloc(&ws.counters, 32 * sizeof(unsigned long long)));
   for (int i = 0; i < 4; i++)
     if (!ws.ev[i]) CUDA_TRY(cudaEventCreate(&ws.ev[i]));
   P.basis_rm = ws.basis_rm, P.basis_cm = ws.basis_cm, P.dbasis_cm = ws.dbasis_cm;
@@ -611,7 +630,7 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
   P.decaybasis = o->decaybasis;
   P.sfr = o->sfr, P.sgm = o->sgm, P.mfr = o->mfr, P.mgm = o->mgm;
   DeviceWs &ws = g_ws[dev];
-  CUDA_TRY(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream));
+  CUDA_TRY(cudaMemsetAsync(ws.counters, 0, 32 * sizeof(unsigned long long), stream));
   CUDA_TRY(cudaEventRecord(ws.ev[0], stream));
   int nt = plan.S.nA * plan.S.nT2;
   basis_setup_kernel<<<(nt + 63) / 64, 64, 0, stream>>>(plan.S);
@@ -642,11 +661,31 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
   float a = 0, b = 0;
   CUDA_TRY(cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]));
   CUDA_TRY(cudaEventElapsedTime(&b, ws.ev[1], ws.ev[2]));
-  unsigned long long c[8];
+  unsigned long long c[32];
   CUDA_TRY(cudaMemcpy(c, ws.counters, sizeof c, cudaMemcpyDeviceToHost));
   st->setup_ms = std::max(st->setup_ms, (double)a);
   st->pipeline_ms = std::max(st->pipeline_ms, (double)b);
   st->voxels_processed += (int64_t)c[1];
+  if (getenv("DECAES_PHASE_CYCLES"))
+    fprintf(stderr, "[decaes] warp-cycles per voxel: barrier %.0f  flip-angle %.0f  basis %.0f  solve+save %.0f\n",
+            (double)c[4] / std::max<double>(1.0, (double)c[1]), (double)c[5] / std::max<double>(1.0, (double)c[1]),
+            (double)c[6] / std::max<double>(1.0, (double)c[1]), (double)c[7] / std::max<double>(1.0, (double)c[1]));
+#ifdef DECAES_PROFILE
+  if (getenv("DECAES_PHASE_CYCLES")) {
+    const char *nm[PF_COUNT] = {"rhs", "nnls_unreg", "resid", "refine", "grad", "stage", "suggest", "epg", "build", "nnls_tikh", "lc_book", "save"};
+    for (int i = 0; i < PF_COUNT; i++) fprintf(stderr, "  %-10s %9.0f\n", nm[i], (double)c[8 + i] / std::max<double>(1.0, (double)c[1]));
+    unsigned long long gp[16];
+    cudaMemcpyFromSymbol(gp, g_prof, sizeof gp);
+    const char *gn[4] = {"append", "rebuild", "dual", "nnls"};
+    double nv = std::max<double>(1.0, (double)c[1]);
+    for (int i = 0; i < 4; i++)
+      fprintf(stderr, "  gram %-8s cycles/voxel %9.0f  calls/voxel %7.1f  cycles/call %7.0f\n", gn[i], gp[i] / nv, gp[4 + i] / nv,
+              gp[4 + i] ? (double)gp[i] / gp[4 + i] : 0.0);
+    fprintf(stderr, "  mean k at append %.1f\n", gp[4] ? (double)gp[8] / gp[4] : 0.0);
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_prof, z, sizeof z);
+  }
+#endif
   st->kernel_launches += 3;
   ws.ev_pending = false;
   return DECAES_OK;

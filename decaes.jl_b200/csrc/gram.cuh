@@ -24,6 +24,15 @@
 
 namespace decaes {
 
+#ifdef DECAES_PROFILE
+__device__ unsigned long long g_prof[16];  // [0..3] cycles append/rebuild/dual/nnls, [4..7] calls, [8] sum k at append
+#define GP_BEGIN() long long gp_t0 = clock64()
+#define GP_END(id) if (lane_id() == 0) { atomicAdd(&g_prof[id], (unsigned long long)(clock64() - gp_t0)); atomicAdd(&g_prof[4 + id], 1ull); }
+#else
+#define GP_BEGIN()
+#define GP_END(id)
+#endif
+
 struct GramProb {
   double *T;        // combined G / M array in shared memory
   int ld;
@@ -71,7 +80,7 @@ __device__ __forceinline__ unsigned long long mask_of(const int *P, int k) {
 // Append column j to the factorisation (pivot position k).  Returns false (and changes nothing)
 // when the column is numerically dependent (d^2 <= 0) or, with `need_positive`, when its
 // coefficient would not be positive (the reference's b1/A1 > 0 test).
-__device__ __noinline__ bool gram_append(const GramProb &p, const GramWs &ws, int &k, int j, bool need_positive) {
+__device__ __forceinline__ bool gram_append(const GramProb &p, const GramWs &ws, int &k, int j, bool need_positive) {
   const int lane = lane_id();
   double *T = p.T;
   const int ld = p.ld;
@@ -93,10 +102,14 @@ __device__ __noinline__ bool gram_append(const GramProb &p, const GramWs &ws, in
     ll = fma(lt, lt, ll);
     ly = fma(lt, ws.y[t], ly);
   }
-  ll = warp_sum(ll), ly = warp_sum(ly);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {  // both sums ride the same butterfly
+    ll += __shfl_xor_sync(DECAES_FULL_MASK, ll, o);
+    ly += __shfl_xor_sync(DECAES_FULL_MASK, ly, o);
+  }
   const double d2 = (T[j * ld + j] + p.mu2) - ll;
   if (!(d2 > 0.0)) return false;
-  const double dinv = drsqrt(d2);
+  const double dinv = rsqrt(d2);
   const double ynew = (p.c[j] - ly) * dinv;
   if (need_positive && !(ynew > 0.0)) return false;
   __syncwarp();
@@ -126,7 +139,7 @@ __device__ __noinline__ bool gram_append(const GramProb &p, const GramWs &ws, in
 }
 
 // Rebuild rows [from, k) of M (after a removal or for a warm start); P[0:k) already holds the columns.
-__device__ __noinline__ void gram_rebuild(const GramProb &p, const GramWs &ws, int &k, int from) {
+__device__ __forceinline__ void gram_rebuild(const GramProb &p, const GramWs &ws, int &k, int from) {
   const int lane = lane_id();
   const int kold = k, ld = p.ld;
   double *T = p.T;
@@ -149,8 +162,9 @@ __device__ __noinline__ void gram_rebuild(const GramProb &p, const GramWs &ws, i
   }
 }
 
+
 // w_j = c_j - sum_t G(P[t], j) * s_t for every column; entries of active columns are forced to 0.
-__device__ __noinline__ void gram_dual(const GramProb &p, const GramWs &ws, int k, unsigned long long mask) {
+__device__ __forceinline__ void gram_dual(const GramProb &p, const GramWs &ws, int k, unsigned long long mask) {
   const int lane = lane_id();
   _Pragma("unroll 1") for (int j = lane; j < p.n; j += 32) {
     double a0 = p.c[j], a1 = 0.0;
@@ -168,7 +182,9 @@ __device__ __noinline__ void gram_dual(const GramProb &p, const GramWs &ws, int 
 
 // Lawson–Hanson main loop.  cold: start from the empty set with the reference's warm dual
 // (src/lsqnonneg.jl:44-70).  warm: start from the feasible point ws.x supported on `mask`.
-__device__ __noinline__ GramOut gram_nnls(const GramProb &p, const GramWs &ws, bool warm, unsigned long long mask) {
+__device__ __noinline__ GramOut gram_nnls(const GramProb &p_in, const GramWs &ws_in, bool warm, unsigned long long mask) {
+  const GramProb p = p_in;  // copies: keep every pointer in registers instead of reloading it from the caller's frame
+  const GramWs ws = ws_in;
   const int lane = lane_id();
   const int n = p.n;
   int k = 0, iter = 0;

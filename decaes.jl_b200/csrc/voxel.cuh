@@ -37,6 +37,8 @@ struct PipeParams {
   const double *gram_set;   // [nA][nT2*ldg]     A_k'A_k per grid angle (Gram solver)
   int gram, ldg;            // solver variant (1 = normal-equation active set), leading dimension of G
   int warps_per_cta, smem_per_warp;  // CTA shape: bytes of dynamic shared memory owned by each warp
+  int fa_warm;              // warm-start flip-angle probes from the nearest probed angle (Gram solver)
+  int sync_mask;            // which intra-round CTA barriers are active (bit 0: after flip angle, bit 1: after basis)
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
   double angles[DECAES_MAX_ANGLES];                            // flip-angle grid (degrees)
   double logT2[DECAES_MAX_NT2], E2[DECAES_MAX_NT2];            // log(T2_j), exp(-(TE/2)/T2_j)
@@ -49,7 +51,7 @@ struct PipeParams {
 
 // layout of the per-warp global scratch (in doubles)
 struct ScratchLayout {
-  int pristine, pristine_cm, slots_x, lc_pts, lc_states, fa_u, fa_du, gcv_gamma, gcv_mat, total;
+  int pristine, pristine_cm, slots_x, lc_pts, lc_states, fa_u, fa_du, fa_mask, gcv_gamma, gcv_mat, total;
   __host__ __device__ ScratchLayout(int nTE, int nT2, int copy_elems, bool gcv) {
     int o = 0;
     pristine = o, o += copy_elems;
@@ -59,6 +61,7 @@ struct ScratchLayout {
     lc_states = o, o += DECAES_LC_MAX * 6;
     fa_u = o, o += DECAES_MAX_ANGLES;
     fa_du = o, o += DECAES_MAX_ANGLES;
+    fa_mask = o, o += DECAES_MAX_ANGLES;
     gcv_gamma = o, o += (nTE < nT2 ? nTE : nT2);
     gcv_mat = o, o += gcv ? nTE * nT2 : 0;
     total = (o + 1) & ~1;
@@ -68,11 +71,11 @@ struct ScratchLayout {
 // per-warp shared memory layout (in doubles, then ints)
 struct SmemLayout {
   int A, b, u, x, w, bd, sig, fit, slot_mu, slot_r2, slot_x2, slot_mask, idx, bar, total_bytes;
-  int M, c, y, s, t1, t2;  // Gram solver only
+  int M, c, y, s, t1, t2, lc_pts, lc_states, slots_x, fa_u, fa_du, fa_mask;  // Gram solver only
   __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems, int gram) {
     int o = 0;
     A = o, o += a_elems;  // QR: working matrix / EPG scratch.  Gram: combined G / M array (nT2 x ldg)
-    b = u = M = c = y = s = t1 = t2 = 0;
+    b = u = M = c = y = s = t1 = t2 = lc_pts = lc_states = slots_x = fa_u = fa_du = fa_mask = 0;
     if (gram) {
       M = 0;  // M lives in the strictly-upper part of the G array (gram.cuh)
       c = o, o += nT2;
@@ -80,6 +83,12 @@ struct SmemLayout {
       s = o, o += nT2;
       t1 = o, o += nT2;
       t2 = o, o += nT2;
+      lc_pts = o, o += 4 * DECAES_LC_MAX;
+      lc_states = o, o += 6 * DECAES_LC_MAX;
+      slots_x = o, o += DECAES_NCACHE * nT2;
+      fa_u = o, o += DECAES_MAX_ANGLES;
+      fa_du = o, o += DECAES_MAX_ANGLES;
+      fa_mask = o, o += DECAES_MAX_ANGLES;
     } else {
       b = o, o += rows_alloc;
       u = o, o += rows_alloc;
@@ -106,14 +115,29 @@ struct Src {               // where the current basis of the Gram solver lives
   const double *Acm;       // column-major [col * nTE + i]
 };
 
+#ifdef DECAES_PROFILE
+#define PROF_BEGIN(id) long long prof_t0_##id = clock64()
+#define PROF_END(id) prof_cyc[id] += clock64() - prof_t0_##id
+#else
+#define PROF_BEGIN(id)
+#define PROF_END(id)
+#endif
+enum { PF_RHS = 0, PF_NNLS_UNREG, PF_RESID, PF_REFINE, PF_GRAD, PF_STAGE, PF_SUGGEST, PF_EPG, PF_BUILD, PF_NNLS_TIKH,
+       PF_LC_BOOK, PF_SAVE, PF_COUNT };
+
 template <bool GRAM>
 struct Warp {
+  long long prof_cyc[PF_COUNT] = {0};
   Src cursrc;
   const PipeParams &P;
   NnlsWs ws;
   GramWs gws;                    // Gram solver scratch
   double *Gs, *cvec;             // per-voxel G = A'A and c = A'b in shared memory (Gram solver)
   unsigned long long *slot_mask; // active set of each cache slot
+  // small control tables: shared memory for the Gram solver (an L2 round trip per access would
+  // dominate the latency of the scalar search code), global scratch for the QR port
+  double *lc_pts_p, *lc_states_p, *slots_x_p, *fa_u_p, *fa_du_p;
+  unsigned long long *fa_mask_p;
   double *bd, *sig, *fit, *slot_mu, *slot_r2, *slot_x2;
   uint64_t *bar;
   unsigned phase;
@@ -134,6 +158,13 @@ struct Warp {
     gws.y = smem + L.y, gws.s = smem + L.s, gws.x = smem + L.x, gws.w = smem + L.w;
     gws.t1 = smem + L.t1, gws.t2 = smem + L.t2, gws.P = (int *)(smem + L.idx);
     slot_mask = (unsigned long long *)(smem + L.slot_mask);
+    if (p.gram) {
+      lc_pts_p = smem + L.lc_pts, lc_states_p = smem + L.lc_states, slots_x_p = smem + L.slots_x;
+      fa_u_p = smem + L.fa_u, fa_du_p = smem + L.fa_du, fa_mask_p = (unsigned long long *)(smem + L.fa_mask);
+    } else {
+      lc_pts_p = gscratch + sl.lc_pts, lc_states_p = gscratch + sl.lc_states, slots_x_p = gscratch + sl.slots_x;
+      fa_u_p = gscratch + sl.fa_u, fa_du_p = gscratch + sl.fa_du, fa_mask_p = (unsigned long long *)(gscratch + sl.fa_mask);
+    }
     bd = smem + L.bd, sig = smem + L.sig, fit = smem + L.fit;
     slot_mu = smem + L.slot_mu, slot_r2 = smem + L.slot_r2, slot_x2 = smem + L.slot_x2;
     bar = (uint64_t *)(smem + L.bar);
@@ -223,7 +254,7 @@ struct Warp {
   // suggest_point  src/splines.jl:544-566.  Pieces are evaluated in parallel (lane <-> piece);
   // "first strictly smaller wins" of the sequential scan = lexicographic min over (value, order).
   __device__ __noinline__ void suggest_point(unsigned long long seen, double &xs, double &us) {
-    const double *fu = g + sl.fa_u, *fdu = g + sl.fa_du;
+    const double *fu = fa_u_p, *fdu = fa_du_p;
     int npts = __popcll(seen);
     double bestu = CUDART_INF, bestx = 0.0;
     int besto = 0x7fffffff;
@@ -263,9 +294,13 @@ struct Warp {
   // EPG basis at `alpha` for this voxel (+ Gram matrix and right-hand side for the Gram solver)
   __device__ void basis_at(double alpha, long long v) {
     if constexpr (GRAM) {
+      PROF_BEGIN(7);
       if (P.nTE <= 63) epg_basis_shfl<false>(alpha, v);
       else epg_basis_shfl<true>(alpha, v);
+      PROF_END(7);
+      PROF_BEGIN(8);
       gram_build(g + sl.pristine);
+      PROF_END(8);
       cursrc.G = Gs, cursrc.ldg = P.ldg, cursrc.Arm = g + sl.pristine, cursrc.Acm = g + sl.pristine_cm;
     } else {
       epg_basis(alpha, v);
@@ -274,9 +309,9 @@ struct Warp {
 
   __device__ void fa_probe(int I, unsigned long long &seen, int &numeval) {
     double u, du;
-    if constexpr (GRAM) fa_eval_gram(I, u, du);
+    if constexpr (GRAM) fa_eval_gram(I, u, du, seen);
     else fa_eval(I, u, du);
-    if (lane == 0) g[sl.fa_u + I] = u, g[sl.fa_du + I] = du;
+    if (lane == 0) fa_u_p[I] = u, fa_du_p[I] = du;
     __syncwarp();
     seen |= (1ull << I);
     numeval++;
@@ -436,7 +471,7 @@ struct Warp {
     nnls_warm_start<true>(ws, bd, mu, dirty_rows);
     NnlsOut o = nnls_core<true>(ws, mu);
     dirty_rows = o.rows_used - P.nTE;
-    double *sx = g + sl.slots_x + cur_slot * P.nT2;
+    double *sx = slots_x_p + cur_slot * P.nT2;
     for (int j = lane; j < P.nT2; j += 32) sx[j] = ws.x[j];
     if (lane == 0) slot_mu[cur_slot] = mu, slot_r2[cur_slot] = o.rnorm_sq, slot_x2[cur_slot] = o.xnorm_sq;
     __syncwarp();
@@ -479,7 +514,7 @@ struct Warp {
 
   // first index i with isapprox(t, key_i), or INT_MAX
   __device__ __noinline__ int lc_find(double t, int npts) {
-    const double *pts = g + sl.lc_pts;
+    const double *pts = lc_pts_p;
     int found = 0x7fffffff;
     for (int i = lane; i < npts; i += 32)
       if (isapprox(t, pts[4 * i])) {
@@ -496,7 +531,7 @@ struct Warp {
 
   // cached evaluation of P(t) = (log ||Ax-b||^2, log ||x||^2); returns the point-cache index
   __device__ __noinline__ int lc_eval(double t, int &npts, const double *Asrc) {
-    double *pts = g + sl.lc_pts;
+    double *pts = lc_pts_p;
     int i = lc_find(t, npts);
     if (i != 0x7fffffff) return i;
     cache_solve(dexp(t), Asrc);
@@ -515,7 +550,7 @@ struct Warp {
 
   __device__ __noinline__ void lc_update_curvature(const double *sx, const int *si, int npts, double tlx, double tly, double brx,
                                       double bry, double Ctol) {
-    double *pts = g + sl.lc_pts;
+    double *pts = lc_pts_p;
     for (int q = 0; q < 4; q++) {
       int pi = si[q];
       double x = sx[q], px = pts[4 * pi + 1], py = pts[4 * pi + 2];
@@ -544,7 +579,7 @@ struct Warp {
 
   // mapfindmax over the curvatures: first maximum under Base.isless (NaN is maximal)
   __device__ __noinline__ int lc_argmax(int npts) {
-    const double *pts = g + sl.lc_pts;
+    const double *pts = lc_pts_p;
     int bi = 0x7fffffff;
     double bc = 0.0;
     for (int i = lane; i < npts; i += 32) {
@@ -566,7 +601,7 @@ struct Warp {
   // an interior point, the sequential scan ends on the LAST one of minimal width, provided that width
   // does not exceed the current state's.  Returns its index or -1.
   __device__ __noinline__ int lc_backtrack(double xb, double wcur, int nst) {
-    const double *sts = g + sl.lc_states;
+    const double *sts = lc_states_p;
     double bw = CUDART_INF;
     int bk = -1;
     for (int k = lane; k < nst; k += 32) {
@@ -589,7 +624,7 @@ struct Warp {
 
   __device__ __noinline__ double lcurve_corner(const double *Asrc) {
     const double phi = 1.618033988749895, xtol = 1e-4, Ptol = 1e-4, Ctol = 1e-4;
-    double *pts = g + sl.lc_pts, *sts = g + sl.lc_states;
+    double *pts = lc_pts_p, *sts = lc_states_p;
     int npts = 0, nst = 0;
     double sx[4];
     int si[4];
@@ -962,32 +997,65 @@ struct Warp {
 
   // unregularised NNLS following the reference's cold-start path, polished by one refinement step;
   // returns ||A x - b||^2 (explicit) and leaves r in `fit`, x in gws.x, the active set in gws.P.
-  __device__ __noinline__ double gram_solve_unreg(const Src &src, GramOut &o) {
+  // `warm_mask` != 0: start from that active set instead (flip-angle probes only: the loss and its
+  // gradient depend on the minimiser, which is unique, not on the pivoting path).
+  __device__ __noinline__ double gram_solve_unreg(const Src &src, GramOut &o, unsigned long long warm_mask = 0ull) {
     GramProb pr;
     pr.T = Gs, pr.ld = P.ldg, pr.c = cvec, pr.mu2 = 0.0, pr.n = P.nT2;
     pr.max_set = P.nTE < P.nT2 ? P.nTE : P.nT2;
-    o = gram_nnls(pr, gws, false, 0ull);
+    if (warm_mask) {
+      _Pragma("unroll 1") for (int j = lane; j < P.nT2; j += 32) gws.x[j] = ((warm_mask >> j) & 1ull) ? 1.0 : 0.0;
+      __syncwarp();
+      PROF_BEGIN(1);
+      o = gram_nnls(pr, gws, true, warm_mask);
+      PROF_END(1);
+    } else {
+      PROF_BEGIN(1);
+      o = gram_nnls(pr, gws, false, 0ull);
+      PROF_END(1);
+    }
+    PROF_BEGIN(2);
     double r2 = gram_residual(src.Acm, o.k);
+    PROF_END(2);
     if (o.k > 0) {
+      PROF_BEGIN(3);
       gram_refine(src.Acm, o.k, 0.0);
+      PROF_END(3);
+      PROF_BEGIN(2);
       r2 = gram_residual(src.Acm, o.k);
+      PROF_END(2);
     }
     return r2;
   }
 
   // loss_with_grad!  src/splines.jl:1010-1041 on grid angle k
-  __device__ __noinline__ void fa_eval_gram(int kang, double &u, double &du) {
+  __device__ __noinline__ void fa_eval_gram(int kang, double &u, double &du, unsigned long long seen) {
     const int nTE = P.nTE, n = P.nT2;
     Src src;
     src.G = P.gram_set + (size_t)kang * P.a_elems, src.ldg = P.ldg;
     src.Arm = P.basis_rm + (size_t)kang * P.copy_elems;
     src.Acm = P.basis_cm + (size_t)kang * nTE * n;
+    PROF_BEGIN(5);
     stage_bulk(Gs, src.G, (unsigned)(P.a_elems * 8));  // TMA: G_k (lower triangle valid) -> shared memory
+    PROF_END(5);
+    PROF_BEGIN(0);
     gram_rhs(src.Arm);
+    PROF_END(0);
+    // warm start from the active set found at the nearest angle already probed
+    unsigned long long warm = 0ull;
+    if (seen && P.fa_warm) {
+      unsigned long long below = seen & ((1ull << kang) - 1ull), above = seen >> kang;  // bit kang itself is never set
+      int jb = below ? 63 - __clzll((long long)below) : -1000;
+      int ja = above ? kang + __ffsll((long long)above) - 1 : 1000;
+      int jn = (kang - jb <= ja - kang) ? jb : ja;
+      warm = fa_mask_p[jn];
+    }
     GramOut o;
-    u = gram_solve_unreg(src, o);
+    u = gram_solve_unreg(src, o, warm);
+    if (lane == 0) fa_mask_p[kang] = o.mask;
     const double *dAk = P.dbasis_cm + (size_t)kang * nTE * n;
     double acc = 0.0;
+    PROF_BEGIN(4);
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
       double dax = 0.0;
       for (int t = 0; t < o.k; t++)
@@ -995,6 +1063,7 @@ struct Warp {
       acc = fma(dax, -fit[i], acc);  // A x - b = -r
     }
     du = 2.0 * warp_sum(acc);
+    PROF_END(4);
   }
 
   // EPG basis at the fitted angle, phase states in registers: lane <-> state index, shifts are warp
@@ -1129,14 +1198,20 @@ struct Warp {
     pr.T = Gs, pr.ld = P.ldg, pr.c = cvec, pr.mu2 = __dmul_rn(mu, mu), pr.n = n, pr.max_set = n;
     GramOut o;
     if (nearest >= 0) {
-      const double *sx = g + sl.slots_x + nearest * n;
+      const double *sx = slots_x_p + nearest * n;
       _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = sx[j];
       __syncwarp();
+      PROF_BEGIN(9);
       o = gram_nnls(pr, gws, true, slot_mask[nearest]);
+      PROF_END(9);
     } else {
+      PROF_BEGIN(9);
       o = gram_nnls(pr, gws, false, 0ull);
+      PROF_END(9);
     }
+    PROF_BEGIN(2);
     double r2 = gram_residual(src.Acm, o.k);
+    PROF_END(2);
     if (o.k > 0 && P.refine_tikh) {
       // one refinement step on the explicit residual: x(mu) accurate to ~cond([A; mu I]) * eps, so
       // that ||Ax - b||^2 and ||x||^2 (the inputs of the mu searches) carry reference-level noise
@@ -1146,7 +1221,7 @@ struct Warp {
       for (int t = lane; t < o.k; t += 32) acc = fma(gws.s[t], gws.s[t], acc);
       o.xnorm_sq = warp_sum(acc);
     }
-    double *sx = g + sl.slots_x + cur_slot * n;
+    double *sx = slots_x_p + cur_slot * n;
     _Pragma("unroll 1") for (int j = lane; j < n; j += 32) sx[j] = gws.x[j];
     if (lane == 0)
       slot_mu[cur_slot] = mu, slot_r2[cur_slot] = r2, slot_x2[cur_slot] = o.xnorm_sq, slot_mask[cur_slot] = o.mask;
@@ -1281,7 +1356,7 @@ struct Warp {
     // save_results!  src/T2mapSEcorr.jl:512-591
     double *xs = ws.w;  // dual no longer needed
     {
-      const double *sx = g + sl.slots_x + cur_slot * n;
+      const double *sx = slots_x_p + cur_slot * n;
       for (int j = lane; j < n; j += 32) {
         double xv = (src_kind == 0) ? ws.x[j] : (src_kind == 1 ? sx[j] : 0.0);
         xs[j] = __dmul_rn(xv, max_signal);
@@ -1290,7 +1365,7 @@ struct Warp {
     double r2 = 0.0, rs = 0.0;
     // residual scratch: the QR path has the Householder vector buffer; the Gram path borrows the
     // L-curve point cache in global scratch, which is free by now (4 * DECAES_LC_MAX >= nTE doubles)
-    double *resv = GRAM ? (g + sl.lc_pts) : ws.u;
+    double *resv = GRAM ? (lc_pts_p) : ws.u;
     if constexpr (GRAM) {
       const double *Acm = cursrc.Acm;
       for (int i = lane; i < nTE; i += 32) {
