@@ -60,6 +60,7 @@ def lib():
                                                C.c_double, C.c_uint64, vp]
         L.decaes_get_stats.argtypes = [C.POINTER(RunStats)]
         L.decaes_measure_fp64_peak.argtypes = [dp]
+        L.decaes_slab_bounds.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         for name in _abi.DECLARED_SYMBOLS:
             getattr(L, name)  # AttributeError if the header and the library disagree
         _lib = L
@@ -317,6 +318,13 @@ def t2part_device(d_dist_ptr, nvox, stride, cpart: T2partOpts, sfr, sgm, mfr, mg
 
 def mock_image_device(d_image_ptr, nvox, stride, first_voxel, nTE, TE, T1=1.0, SNR=60.0, seed=1, stream=0):
     _check(lib().decaes_mock_image_device(d_image_ptr, nvox, stride, first_voxel, nTE, TE, T1, SNR, seed, stream))
+
+
+def slab_bounds(nvox, nshards, index):
+    """Voxel range [v0, v1) of shard `index` (decaes_slab_bounds): how volumes are split over GPUs / ranks."""
+    v0, v1 = C.c_int64(), C.c_int64()
+    _check(lib().decaes_slab_bounds(nvox, nshards, index, C.byref(v0), C.byref(v1)))
+    return v0.value, v1.value
 
 
 def measure_fp64_peak():

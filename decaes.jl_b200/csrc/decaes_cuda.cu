@@ -694,6 +694,15 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
 extern "C" {
 
 const char *decaes_last_error(void) { return g_err; }
+
+int decaes_slab_bounds(int64_t nvox, int32_t nshards, int32_t index, int64_t *v0, int64_t *v1) {
+  if (nvox < 0 || nshards < 1 || index < 0 || index >= nshards || !v0 || !v1)
+    return fail(DECAES_EINVAL, "bad slab arguments");
+  const int64_t g = DECAES_GROUP;
+  *v0 = (nvox * index / nshards) & ~(g - 1);
+  *v1 = (index == nshards - 1) ? nvox : ((nvox * (index + 1) / nshards) & ~(g - 1));
+  return DECAES_OK;
+}
 int decaes_abi_version(void) { return DECAES_ABI_VERSION; }
 
 int decaes_device_count(void) {
@@ -909,7 +918,8 @@ int decaes_t2map(const double *image, const decaes_t2map_opts *opts, const decae
   std::vector<SlabJob> jobs(ng);
   // contiguous voxel slabs, boundaries aligned to the 4-voxel work group
   for (int d = 0; d < ng; d++) {
-    int64_t a = (Nvox * d / ng) & ~(int64_t)(DECAES_GROUP - 1), b = (d == ng - 1) ? Nvox : ((Nvox * (d + 1) / ng) & ~(int64_t)(DECAES_GROUP - 1));
+    int64_t a = 0, b = 0;
+    decaes_slab_bounds(Nvox, ng, d, &a, &b);
     jobs[d].dev = (ng == 1) ? cur : d, jobs[d].v0 = a, jobs[d].v1 = b, jobs[d].rc = 0, jobs[d].err[0] = 0;
   }
   auto worker = [&](SlabJob &j) {

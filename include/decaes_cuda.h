@@ -20,9 +20,10 @@
  *     it out: image (nx,ny,nz,nTE) => voxel v, echo e at image[v + e*Nvox], Nvox=nx*ny*nz;
  *     dist (nx,ny,nz,nT2) => dist[v + j*Nvox]; maps (nx,ny,nz) => map[v].
  *   - Host entry points (decaes_t2map / decaes_t2part) take HOST pointers owned by the
- *     caller, are blocking, shard voxel slabs over `ngpus` devices with no collective,
- *     and write ONLY voxels with image[v,0] > Threshold, so the caller's NaN pre-fill
- *     (src/T2mapSEcorr.jl:36-52, tfill(NaN)) keeps "skipped voxel = NaN".
+ *     caller, are blocking and shard voxel slabs over `ngpus` devices with no collective.
+ *     Voxels with image[v,0] <= Threshold are written as NaN — what the reference's
+ *     NaN pre-fill (src/T2mapSEcorr.jl:36-52, tfill(NaN)) leaves for skipped voxels;
+ *     `alpha` keeps the caller's value there when alpha_provided = 1.
  *   - *_device entry points take DEVICE pointers on the current CUDA device and enqueue
  *     on the given stream (cudaStream_t passed as void*); they do not synchronise.
  *   - Return value: 0 on success, negative decaes_status on failure; the message is in
@@ -145,6 +146,11 @@ int decaes_t2part_device(const double *d_dist, int64_t nvox, int64_t stride,
 int decaes_mock_image_device(double *d_image, int64_t nvox, int64_t stride, int64_t first_voxel,
                              int32_t nTE, double TE, double T1, double SNR, uint64_t seed,
                              void *stream);
+
+/* Voxel slab [*v0, *v1) owned by shard `index` of `nshards` (contiguous, boundaries aligned to the
+ * 4-voxel work group; the last shard takes the remainder).  Pure host arithmetic: this is the
+ * whole multi-GPU "protocol" of the path — shards are independent and there is no collective. */
+int decaes_slab_bounds(int64_t nvox, int32_t nshards, int32_t index, int64_t *v0, int64_t *v1);
 
 /* ---- misc ---- */
 const char *decaes_last_error(void);
