@@ -25,7 +25,8 @@ __all__ = ["T2mapOptions", "T2partOptions", "T2mapSEcorr", "T2partSEcorr", "lib"
            "last_stats", "device_count"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdecaes_cuda.so")
+# DECAES_LIB: developer override (e.g. an instrumented -DDECAES_PROFILE build next to the product library)
+LIB_PATH = os.environ.get("DECAES_LIB") or os.path.join(_HERE, "libdecaes_cuda.so")
 _lib = None
 
 

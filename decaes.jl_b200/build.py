@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdecaes_cuda.so")
 SOURCES = ["decaes_cuda.cu"]
-HEADERS = ["common.cuh", "nnls.cuh", "voxel.cuh", os.path.join("..", "..", "include", "decaes_cuda.h")]
+HEADERS = ["common.cuh", "nnls.cuh", "gram.cuh", "voxel.cuh", os.path.join("..", "..", "include", "decaes_cuda.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -33,15 +33,15 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not is_stale():
+def build(force=False, verbose=False, extra=(), out=None):
+    if out is None and not force and not is_stale():
         return LIB
     nvcc = nvcc_path()
     if nvcc is None:
         if os.path.exists(LIB):
             return LIB
         raise RuntimeError("nvcc not found and libdecaes_cuda.so has not been built")
-    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
@@ -50,4 +50,10 @@ def build(force=False, verbose=False, extra=()):
 
 if __name__ == "__main__":
     import sys
-    build(force=True, verbose=True, extra=sys.argv[1:])
+    args = sys.argv[1:]
+    out = None
+    if "--out" in args:  # e.g. --out /tmp/libdecaes_prof.so -DDECAES_PROFILE
+        i = args.index("--out")
+        out = args[i + 1]
+        del args[i:i + 2]
+    build(force=True, verbose=True, extra=args, out=out)

@@ -185,6 +185,17 @@ __device__ __forceinline__ void gram_dual(const GramProb &p, const GramWs &ws, i
 __device__ __noinline__ GramOut gram_nnls(const GramProb &p_in, const GramWs &ws_in, bool warm, unsigned long long mask) {
   const GramProb p = p_in;  // copies: keep every pointer in registers instead of reloading it from the caller's frame
   const GramWs ws = ws_in;
+  // every one of these lives in shared memory: without the hint the compiler emits generic LD/ST
+  // (plus uniform-register descriptor shuffling) instead of LDS/STS in the hottest loops
+  __builtin_assume(__isShared(p.T));
+  __builtin_assume(__isShared(p.c));
+  __builtin_assume(__isShared(ws.y));
+  __builtin_assume(__isShared(ws.s));
+  __builtin_assume(__isShared(ws.x));
+  __builtin_assume(__isShared(ws.w));
+  __builtin_assume(__isShared(ws.t1));
+  __builtin_assume(__isShared(ws.t2));
+  __builtin_assume(__isShared(ws.P));
   const int lane = lane_id();
   const int n = p.n;
   int k = 0, iter = 0;
