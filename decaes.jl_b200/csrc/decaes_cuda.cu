@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
   const long long ngroups = (P.nvox + DECAES_GROUP - 1) / DECAES_GROUP;
   unsigned long long processed = 0;
   long long cyc[4] = {0, 0, 0, 0};  // per-warp cycles: barrier wait, flip angle, basis, solve+save
+  const long long t_begin = clock64();
   long long v0 = 0;
   int q = DECAES_GROUP;  // next voxel of the current group (DECAES_GROUP = group exhausted)
   bool more_groups = true;
@@ -174,15 +175,7 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
           more_groups = false;
           break;
         }
-        v0 = (long long)gidx * DECAES_GROUP;
-        // stage the group's signals: lane -> (echo offset, voxel) so that each load instruction
-        // touches 8 full 32-byte sectors (4 consecutive voxels per echo)
-        const int qq = lane & 3, eo = lane >> 2;
-        for (int e = eo; e < P.nTE; e += 8) {
-          long long vv = v0 + qq;
-          W.sig[qq * P.nTE + e] = (vv < P.nvox) ? __ldg(P.image + vv + (long long)e * P.stride) : 0.0;
-        }
-        __syncwarp();
+        v0 = (long long)gidx * DECAES_GROUP;  // 4 consecutive voxels share one 32-byte sector per echo (L2 serves the re-reads)
         q = 0;
       }
       v = v0 + q;
@@ -190,9 +183,9 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
         q = DECAES_GROUP;
         continue;
       }
-      signal = W.sig + q * P.nTE;
+      signal = P.image + v;
       q++;
-      if (signal[0] > P.Threshold) {  // src/T2mapSEcorr.jl:177
+      if (__ldg(signal) > P.Threshold) {  // src/T2mapSEcorr.jl:177
         have = true;
       } else {
         // skipped voxel: outputs are NaN (the reference pre-fills NaN, src/T2mapSEcorr.jl:36-52)
@@ -231,6 +224,7 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
   }
   if (lane == 0) {
     for (int c = 0; c < 4; c++) atomicAdd(&P.counters[4 + c], (unsigned long long)cyc[c]);
+    atomicAdd(&P.counters[24], (unsigned long long)(clock64() - t_begin));
 #ifdef DECAES_PROFILE
     for (int c = 0; c < PF_COUNT; c++) atomicAdd(&P.counters[8 + c], (unsigned long long)W.prof_cyc[c]);
 #endif
@@ -561,6 +555,9 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
 
   SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems, P.gram);
   plan->smem_bytes = L.total_bytes;
+  // the solver block + search caches (everything in front of the voxel's signal) are idle while the basis is built
+  P.epg_smem = P.gram && 3 * P.epg_kmax * 32 <= L.bd;
+  if (const char *e = getenv("DECAES_EPG_SMEM")) P.epg_smem = P.epg_smem && atoi(e);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
   if ((size_t)plan->smem_bytes > prop.sharedMemPerBlockOptin)
@@ -667,21 +664,24 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
   st->pipeline_ms = std::max(st->pipeline_ms, (double)b);
   st->voxels_processed += (int64_t)c[1];
   if (getenv("DECAES_PHASE_CYCLES"))
-    fprintf(stderr, "[decaes] warp-cycles per voxel: barrier %.0f  flip-angle %.0f  basis %.0f  solve+save %.0f\n",
+    fprintf(stderr, "[decaes] warp-cycles per voxel: barrier %.0f  flip-angle %.0f  basis %.0f  solve+save %.0f  total %.0f\n",
             (double)c[4] / std::max<double>(1.0, (double)c[1]), (double)c[5] / std::max<double>(1.0, (double)c[1]),
-            (double)c[6] / std::max<double>(1.0, (double)c[1]), (double)c[7] / std::max<double>(1.0, (double)c[1]));
+            (double)c[6] / std::max<double>(1.0, (double)c[1]), (double)c[7] / std::max<double>(1.0, (double)c[1]),
+            (double)c[24] / std::max<double>(1.0, (double)c[1]));
 #ifdef DECAES_PROFILE
   if (getenv("DECAES_PHASE_CYCLES")) {
     const char *nm[PF_COUNT] = {"rhs", "nnls_unreg", "resid", "refine", "grad", "stage", "suggest", "epg", "build", "nnls_tikh", "lc_book", "save"};
     for (int i = 0; i < PF_COUNT; i++) fprintf(stderr, "  %-10s %9.0f\n", nm[i], (double)c[8 + i] / std::max<double>(1.0, (double)c[1]));
     unsigned long long gp[16];
     cudaMemcpyFromSymbol(gp, g_prof, sizeof gp);
-    const char *gn[4] = {"append", "rebuild", "dual", "nnls"};
+    const char *gn[4] = {"append", "factor", "dual", "nnls"};
     double nv = std::max<double>(1.0, (double)c[1]);
     for (int i = 0; i < 4; i++)
       fprintf(stderr, "  gram %-8s cycles/voxel %9.0f  calls/voxel %7.1f  cycles/call %7.0f\n", gn[i], gp[i] / nv, gp[4 + i] / nv,
               gp[4 + i] ? (double)gp[i] / gp[4 + i] : 0.0);
-    fprintf(stderr, "  mean k at append %.1f\n", gp[4] ? (double)gp[8] / gp[4] : 0.0);
+    fprintf(stderr, "  mean k at append %.1f, at factor %.1f; nnls warm %.1f cold %.1f per voxel, mean final k %.1f, mean inner iters %.2f, factor fallbacks/voxel %.3f\n",
+            gp[4] ? (double)gp[8] / gp[4] : 0.0, gp[5] ? (double)gp[9] / gp[5] : 0.0, gp[11] / nv, gp[12] / nv,
+            gp[7] ? (double)gp[13] / gp[7] : 0.0, gp[7] ? (double)gp[14] / gp[7] : 0.0, gp[15] / nv);
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(g_prof, z, sizeof z);
   }

@@ -9,15 +9,24 @@
 //     G = A'A (+ mu^2 I)   n x n symmetric
 //     c = A'b              n
 //     M = L^-1             inverse Cholesky factor of G_PP in pivot order
-// so that appending a column is two O(k) fma chains per lane plus two warp reductions, the
-// solution is s = M'(M c_P) maintained incrementally, and the dual is w = c - G_P x_P.
+// so that appending a column is two O(k) fma chains per lane, the solution is s = M'(M c_P)
+// maintained incrementally, and the dual is w = c - G_P x_P.
 // The minimiser of the Tikhonov problems (mu > 0) is unique, so those solves may be warm-started
 // from the active set of the nearest mu already solved; unregularised solves follow the
 // reference's cold-start path pivot by pivot and are polished with one step of iterative
 // refinement on the explicit residual (done by the caller, which owns A).
 //
-// Shared-memory layout: ONE n x ld array T (ld = (n+1)|1, odd => both access directions are
-// bank-conflict free) holds the lower triangle of G and, in the strictly-upper part, M:
+// The active sets are small (mean 5-7 columns on the benchmark volumes), so every operation is
+// latency bound and the kernel as a whole is instruction-cache bound (L1.5 I-cache = 32 KB).  The
+// code is therefore written for SIZE: one out-of-line copy of each primitive, plain loops, all
+// shared-memory vectors at compile-time offsets from one base pointer, integer REDUX for the
+// arg-max / arg-min reductions.  Warm starts and removals refactor the (tiny) active block with a
+// lane-parallel symmetric elimination (gram_factor) instead of k sequential appends.
+//
+// Shared-memory layout of one warp (doubles, relative to V):
+//     c[64] y[64] s[64] t1[64] t2[64] x[64] w[64] P[64 ints]  T[n x ld]
+// T (ld = (n+1)|1, odd => both access directions are bank-conflict free) holds the lower triangle
+// of G and, in the strictly-upper part, M:
 //     G(p,q) = T[max(p,q)*ld + min(p,q)]          M(t,u) = T[u*ld + t + 1]   (u <= t)
 #pragma once
 #include "common.cuh"
@@ -25,32 +34,19 @@
 namespace decaes {
 
 #ifdef DECAES_PROFILE
-__device__ unsigned long long g_prof[16];  // [0..3] cycles append/rebuild/dual/nnls, [4..7] calls, [8] sum k at append
+// [0..3] cycles append/factor/dual/nnls, [4..7] calls, [8] sum k at append, [9] sum k at factor,
+// [11] warm calls, [12] cold calls, [13] sum final k, [14] sum inner iterations, [15] factor fallbacks
+__device__ unsigned long long g_prof[16];
 #define GP_BEGIN() long long gp_t0 = clock64()
 #define GP_END(id) if (lane_id() == 0) { atomicAdd(&g_prof[id], (unsigned long long)(clock64() - gp_t0)); atomicAdd(&g_prof[4 + id], 1ull); }
+#define GP_ADD(id, v) if (lane_id() == 0) atomicAdd(&g_prof[id], (unsigned long long)(v))
 #else
 #define GP_BEGIN()
 #define GP_END(id)
+#define GP_ADD(id, v)
 #endif
 
-struct GramProb {
-  double *T;        // combined G / M array in shared memory
-  int ld;
-  const double *c;  // [n] shared memory
-  double mu2;       // mu^2 (0 for the plain problem)
-  int n;
-  int max_set;      // min(m, n) for the plain problem, n for Tikhonov (src/NNLS.jl:627, :851)
-};
-
-struct GramWs {  // shared-memory scratch of one warp
-  double *y;     // [n] y = M c_P
-  double *s;     // [n] s = M' y   (solution on P, in pivot order)
-  double *x;     // [n] current feasible solution, indexed by column
-  double *w;     // [n] dual, indexed by column
-  double *t1;    // [n] scratch
-  double *t2;    // [n] scratch
-  int *P;        // [n] active columns in pivot order
-};
+enum { GV_C = 0, GV_Y = 64, GV_S = 128, GV_T1 = 192, GV_T2 = 256, GV_X = 320, GV_W = 384, GV_P = 448, GV_T = 480 };
 
 struct GramOut {
   int k;                     // number of active columns
@@ -58,11 +54,11 @@ struct GramOut {
   double xnorm_sq;           // sum of squares of the solution
 };
 
-__device__ __forceinline__ double gram_G(const GramProb &p, int a, int b) {
-  int hi = a > b ? a : b, lo = a > b ? b : a;
-  return p.T[hi * p.ld + lo];
-}
 #define GM_(t, u) T[(u) * ld + (t) + 1]
+__device__ __forceinline__ double gram_G(const double *T, int ld, int a, int b) {
+  int hi = a > b ? a : b, lo = a > b ? b : a;
+  return T[hi * ld + lo];
+}
 
 __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
   unsigned lo = __reduce_or_sync(DECAES_FULL_MASK, (unsigned)v);
@@ -72,259 +68,320 @@ __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
 __device__ __forceinline__ unsigned long long mask_of(const int *P, int k) {
   const int lane = lane_id();
   unsigned long long m = 0ull;
-  if (lane < k) m |= 1ull << P[lane];
-  if (lane + 32 < k) m |= 1ull << P[lane + 32];
+  for (int t = lane; t < k; t += 32) m |= 1ull << P[t];
   return warp_or64(m);
 }
 
-// Append column j to the factorisation (pivot position k).  Returns false (and changes nothing)
-// when the column is numerically dependent (d^2 <= 0) or, with `need_positive`, when its
-// coefficient would not be positive (the reference's b1/A1 > 0 test).
-__device__ __forceinline__ bool gram_append(const GramProb &p, const GramWs &ws, int &k, int j, bool need_positive) {
-  const int lane = lane_id();
-  double *T = p.T;
-  const int ld = p.ld;
-  _Pragma("unroll 1") for (int t = lane; t < k; t += 32) ws.t1[t] = gram_G(p, ws.P[t], j);
-  __syncwarp();
-  // l = M g  (lane <-> row t; for fixed u the lanes read consecutive words)
-  double ll = 0.0, ly = 0.0;
-  _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
-    double a0 = 0.0, a1 = 0.0;
-    int u = 0;
-#pragma unroll 1
-    for (; u + 1 <= t; u += 2) {
-      a0 = fma(GM_(t, u), ws.t1[u], a0);
-      a1 = fma(GM_(t, u + 1), ws.t1[u + 1], a1);
-    }
-    if (u <= t) a0 = fma(GM_(t, u), ws.t1[u], a0);
-    double lt = a0 + a1;
-    ws.t2[t] = lt;
-    ll = fma(lt, lt, ll);
-    ly = fma(lt, ws.y[t], ly);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {  // both sums ride the same butterfly
-    ll += __shfl_xor_sync(DECAES_FULL_MASK, ll, o);
-    ly += __shfl_xor_sync(DECAES_FULL_MASK, ly, o);
-  }
-  const double d2 = (T[j * ld + j] + p.mu2) - ll;
-  if (!(d2 > 0.0)) return false;
-  const double dinv = rsqrt(d2);
-  const double ynew = (p.c[j] - ly) * dinv;
-  if (need_positive && !(ynew > 0.0)) return false;
-  __syncwarp();
-  // new row of M: M(k,u) = -dinv * sum_{t >= u} l_t M(t,u)   (lane <-> column u, own row contiguous in t)
-  _Pragma("unroll 1") for (int u = lane; u < k; u += 32) {
-    double a0 = 0.0, a1 = 0.0;
-    int t = u;
-#pragma unroll 1
-    for (; t + 1 < k; t += 2) {
-      a0 = fma(ws.t2[t], GM_(t, u), a0);
-      a1 = fma(ws.t2[t + 1], GM_(t + 1, u), a1);
-    }
-    if (t < k) a0 = fma(ws.t2[t], GM_(t, u), a0);
-    double mu_ = -dinv * (a0 + a1);
-    GM_(k, u) = mu_;
-    ws.s[u] = fma(ynew, mu_, ws.s[u]);
-  }
-  if (lane == 0) {
-    GM_(k, k) = dinv;
-    ws.y[k] = ynew;
-    ws.s[k] = ynew * dinv;
-    ws.P[k] = j;
-  }
-  __syncwarp();
-  k += 1;
-  return true;
+// Arg-max / arg-min of NON-NEGATIVE doubles through their (order-preserving) bit patterns with the
+// integer REDUX unit: three reductions instead of a five-round shuffle butterfly.  `key` is the
+// lane's best candidate (0 / ~0 = none), `idx` its index; ties resolve to the smallest index.
+__device__ __forceinline__ int warp_argmax_bits(unsigned long long key, int idx, unsigned long long &best) {
+  const unsigned hi = __reduce_max_sync(DECAES_FULL_MASK, (unsigned)(key >> 32));
+  const unsigned lo = __reduce_max_sync(DECAES_FULL_MASK, ((unsigned)(key >> 32) == hi) ? (unsigned)key : 0u);
+  best = ((unsigned long long)hi << 32) | lo;
+  return (int)__reduce_min_sync(DECAES_FULL_MASK, (key == best) ? (unsigned)idx : 0x7fffffffu);
+}
+__device__ __forceinline__ int warp_argmin_bits(unsigned long long key, int idx, unsigned long long &best) {
+  const unsigned hi = __reduce_min_sync(DECAES_FULL_MASK, (unsigned)(key >> 32));
+  const unsigned lo = __reduce_min_sync(DECAES_FULL_MASK, ((unsigned)(key >> 32) == hi) ? (unsigned)key : 0xffffffffu);
+  best = ((unsigned long long)hi << 32) | lo;
+  return (int)__reduce_min_sync(DECAES_FULL_MASK, (key == best) ? (unsigned)idx : 0x7fffffffu);
 }
 
-// Rebuild rows [from, k) of M (after a removal or for a warm start); P[0:k) already holds the columns.
-__device__ __forceinline__ void gram_rebuild(const GramProb &p, const GramWs &ws, int &k, int from) {
+// Append column j to the factorisation at pivot position k.  Returns false (and changes nothing)
+// when the column is numerically dependent (d^2 <= 0) or, with `need_positive`, when its
+// coefficient would not be positive (the reference's b1/A1 > 0 test).  The caller increments k.
+__device__ __noinline__ bool gram_append(double *V, int ld, int k, int j, double mu2, bool need_positive) {
+  __builtin_assume(__isShared(V));
   const int lane = lane_id();
-  const int kold = k, ld = p.ld;
-  double *T = p.T;
-  // s = M[0:from]' y[0:from]
-  _Pragma("unroll 1") for (int u = lane; u < kold; u += 32) {
+  double *T = V + GV_T;
+  const int *P = (const int *)(V + GV_P);
+  GP_BEGIN();
+  GP_ADD(8, k);
+  _Pragma("unroll 1") for (int t = lane; t < k; t += 32) V[GV_T1 + t] = gram_G(T, ld, P[t], j);
+  __syncwarp();
+  // l = M g  (lane <-> row t; for fixed u the lanes read consecutive words)
+  _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
     double a = 0.0;
-    for (int t = u; t < from; t++) a = fma(GM_(t, u), ws.y[t], a);
-    ws.s[u] = a;
+    _Pragma("unroll 4") for (int u = 0; u <= t; u++) a = fma(GM_(t, u), V[GV_T1 + u], a);
+    V[GV_T2 + t] = a;
   }
   __syncwarp();
-  k = from;
-  for (int t = from; t < kold; t++) {
-    int j = ws.P[t];
+  // |l|^2 and l'y: every lane sums the k terms in the same order (k is small; cheaper than a butterfly)
+  double ll = 0.0, ly = 0.0;
+  _Pragma("unroll 4") for (int t = 0; t < k; t++) {
+    const double lt = V[GV_T2 + t];
+    ll = fma(lt, lt, ll);
+    ly = fma(lt, V[GV_Y + t], ly);
+  }
+  const double d2 = (T[j * ld + j] + mu2) - ll;
+  bool ok = d2 > 0.0;
+  double dinv = 0.0, ynew = 0.0;
+  if (ok) {
+    dinv = rsqrt(d2);
+    ynew = (V[GV_C + j] - ly) * dinv;
+    ok = !need_positive || ynew > 0.0;
+  }
+  if (ok) {
+    // new row of M: M(k,u) = -dinv * sum_{t >= u} l_t M(t,u)   (lane <-> column u, contiguous in t)
+    _Pragma("unroll 1") for (int u = lane; u < k; u += 32) {
+      double a = 0.0;
+      _Pragma("unroll 4") for (int t = u; t < k; t++) a = fma(V[GV_T2 + t], GM_(t, u), a);
+      const double m = -dinv * a;
+      GM_(k, u) = m;
+      V[GV_S + u] = fma(ynew, m, V[GV_S + u]);
+    }
+    if (lane == 0) {
+      GM_(k, k) = dinv;
+      V[GV_Y + k] = ynew;
+      V[GV_S + k] = ynew * dinv;
+      ((int *)(V + GV_P))[k] = j;
+    }
     __syncwarp();
-    if (!gram_append(p, ws, k, j, false)) {
-      // numerically dependent column inside a set that was independent a moment ago: drop it
-      if (lane == 0) ws.x[j] = 0.0;
+  }
+  GP_END(0);
+  return ok;
+}
+
+// Factor the whole active block at once: M = L^-1 with G_PP + mu2 I = L L', y = M c_P, s = M'y for
+// the k columns listed in P.  Symmetric Gaussian elimination on [K | c | I], lane <-> row, done in
+// place in M's storage: after step p, row i holds the multipliers R(i, 0..p) of the unit lower
+// triangular R = Ltilde^-1 and the still-to-be-eliminated K entries (i, p+1..i).  M = D^-1/2 R.
+// Returns false when a pivot is not positive (numerically dependent set): the caller falls back
+// to sequential appends, which drop the offending column.
+__device__ __noinline__ bool gram_factor(double *V, int ld, int k, double mu2) {
+  __builtin_assume(__isShared(V));
+  const int lane = lane_id();
+  double *T = V + GV_T;
+  const int *P = (const int *)(V + GV_P);
+  GP_BEGIN();
+  GP_ADD(9, k);
+  _Pragma("unroll 1") for (int i = lane; i < k; i += 32) {
+    const int pi = P[i];
+    _Pragma("unroll 1") for (int q0 = 0; q0 < i; q0 += 4) {  // four gathers in flight
+      double g[4];
+      _Pragma("unroll") for (int e = 0; e < 4; e++) g[e] = gram_G(T, ld, pi, P[q0 + e < i ? q0 + e : i]);
+      _Pragma("unroll") for (int e = 0; e < 4; e++)
+        if (q0 + e < i) GM_(i, q0 + e) = g[e];
+    }
+    GM_(i, i) = T[pi * ld + pi] + mu2;
+    V[GV_Y + i] = V[GV_C + pi];
+  }
+  bool ok = true;
+  _Pragma("unroll 1") for (int p = 0; p < k; p++) {
+    // snapshot of column p (rows >= p), double-buffered in t1 / t2 so one barrier per step suffices;
+    // every row stays with the same lane throughout
+    double *col = V + ((p & 1) ? GV_T2 : GV_T1);
+    _Pragma("unroll 1") for (int i = lane; i < k; i += 32)
+      if (i >= p) col[i] = GM_(i, p);
+    __syncwarp();
+    const double d = col[p];
+    if (!(d > 0.0)) {
+      ok = false;
+      break;
+    }
+    const double rinv = __drcp_rn(d), yp = V[GV_Y + p];
+    _Pragma("unroll 1") for (int i = lane; i < k; i += 32) {
+      if (i <= p) continue;
+      const double f = col[i] * rinv;
+      // row_i -= f * (row p of R | column p of K), entries q in [0, i] \ {p}; four at a time so the
+      // loads of a batch are in flight together (the compiler cannot reorder them across the stores)
+      _Pragma("unroll 1") for (int q0 = 0; q0 <= i; q0 += 4) {
+        double a[4], o[4];
+        _Pragma("unroll") for (int e = 0; e < 4; e++) {
+          const int q = q0 + e;
+          const int qq = (q <= i && q != p) ? q : i;
+          a[e] = GM_(i, qq);
+          o[e] = (qq < p) ? GM_(p, qq) : col[qq];
+        }
+        _Pragma("unroll") for (int e = 0; e < 4; e++) {
+          const int q = q0 + e;
+          if (q <= i && q != p) GM_(i, q) = fma(-f, o[e], a[e]);
+        }
+      }
+      GM_(i, p) = -f;
+      V[GV_Y + i] = fma(-f, yp, V[GV_Y + i]);
+    }
+  }
+  __syncwarp();
+  if (ok) {
+    _Pragma("unroll 1") for (int i = lane; i < k; i += 32) {
+      const double dinv = rsqrt(GM_(i, i));
+      _Pragma("unroll 4") for (int q = 0; q < i; q++) GM_(i, q) *= dinv;
+      GM_(i, i) = dinv;
+      V[GV_Y + i] *= dinv;
+    }
+    __syncwarp();
+    _Pragma("unroll 1") for (int u = lane; u < k; u += 32) {
+      double a = 0.0;
+      _Pragma("unroll 4") for (int t = u; t < k; t++) a = fma(GM_(t, u), V[GV_Y + t], a);
+      V[GV_S + u] = a;
+    }
+    __syncwarp();
+  }
+  GP_END(1);
+  return ok;
+}
+
+// (Re)build the factorisation of the columns listed in P[0:k).  Returns the number of columns kept.
+__device__ __noinline__ int gram_refactor(double *V, int ld, int k, double mu2) {
+  if (k == 0 || gram_factor(V, ld, k, mu2)) return k;
+  // numerically dependent set (rare): sequential appends, dropping the offending columns
+  GP_ADD(15, 1);
+  int *P = (int *)(V + GV_P);
+  int kk = 0;
+  for (int t = 0; t < k; t++) {
+    const int j = P[t];
+    __syncwarp();
+    if (gram_append(V, ld, kk, j, mu2, false)) {
+      kk++;
+    } else {
+      if (lane_id() == 0) V[GV_X + j] = 0.0;
       __syncwarp();
     }
   }
-}
-
-
-// w_j = c_j - sum_t G(P[t], j) * s_t for every column; entries of active columns are forced to 0.
-__device__ __forceinline__ void gram_dual(const GramProb &p, const GramWs &ws, int k, unsigned long long mask) {
-  const int lane = lane_id();
-  _Pragma("unroll 1") for (int j = lane; j < p.n; j += 32) {
-    double a0 = p.c[j], a1 = 0.0;
-    int t = 0;
-#pragma unroll 1
-    for (; t + 1 < k; t += 2) {
-      a0 = fma(-gram_G(p, ws.P[t], j), ws.s[t], a0);
-      a1 = fma(-gram_G(p, ws.P[t + 1], j), ws.s[t + 1], a1);
-    }
-    if (t < k) a0 = fma(-gram_G(p, ws.P[t], j), ws.s[t], a0);
-    ws.w[j] = ((mask >> j) & 1ull) ? 0.0 : a0 + a1;
-  }
-  __syncwarp();
+  return kk;
 }
 
 // Lawson–Hanson main loop.  cold: start from the empty set with the reference's warm dual
-// (src/lsqnonneg.jl:44-70).  warm: start from the feasible point ws.x supported on `mask`.
-__device__ __noinline__ GramOut gram_nnls(const GramProb &p_in, const GramWs &ws_in, bool warm, unsigned long long mask) {
-  const GramProb p = p_in;  // copies: keep every pointer in registers instead of reloading it from the caller's frame
-  const GramWs ws = ws_in;
-  // every one of these lives in shared memory: without the hint the compiler emits generic LD/ST
-  // (plus uniform-register descriptor shuffling) instead of LDS/STS in the hottest loops
-  __builtin_assume(__isShared(p.T));
-  __builtin_assume(__isShared(p.c));
-  __builtin_assume(__isShared(ws.y));
-  __builtin_assume(__isShared(ws.s));
-  __builtin_assume(__isShared(ws.x));
-  __builtin_assume(__isShared(ws.w));
-  __builtin_assume(__isShared(ws.t1));
-  __builtin_assume(__isShared(ws.t2));
-  __builtin_assume(__isShared(ws.P));
+// (src/lsqnonneg.jl:44-70).  warm: start from the feasible point x supported on `mask`.
+__device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, int max_set, bool warm, unsigned long long mask) {
+  __builtin_assume(__isShared(V));
   const int lane = lane_id();
-  const int n = p.n;
+  double *T = V + GV_T;
+  int *P = (int *)(V + GV_P);
+  GP_BEGIN();
+  GP_ADD(warm ? 11 : 12, 1);
   int k = 0, iter = 0;
   const int max_iter = 3 * n;
-  bool need_solve_check = false;
+  bool check_first = false;
 
   if (!warm) {
     mask = 0ull;
     // dual as if the last column were active; w[n-1] = 0, or 1 if every other dual is <= 0
-    const double xj = ddiv(p.c[n - 1], p.T[(n - 1) * p.ld + (n - 1)] + p.mu2);
+    const double xj = ddiv(V[GV_C + n - 1], T[(n - 1) * ld + (n - 1)] + mu2);
     bool anypos = false;
     _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
-      double wj = (j < n - 1) ? fma(-gram_G(p, n - 1, j), xj, p.c[j]) : 0.0;
-      ws.w[j] = wj;
-      ws.x[j] = 0.0;
+      const double wj = (j < n - 1) ? fma(-T[(n - 1) * ld + j], xj, V[GV_C + j]) : 0.0;
+      V[GV_W + j] = wj;
+      V[GV_X + j] = 0.0;
       anypos |= !(wj <= 0.0);
     }
-    if (!__any_sync(DECAES_FULL_MASK, anypos) && lane == 0) ws.w[n - 1] = 1.0;
+    if (!__any_sync(DECAES_FULL_MASK, anypos) && lane == 0) V[GV_W + n - 1] = 1.0;
     __syncwarp();
   } else {
-    // factor the inherited set (ascending column order)
-    unsigned long long m2 = mask;
-    int kk = 0;
-    while (m2) {
-      int j = __ffsll((long long)m2) - 1;
-      m2 &= m2 - 1;
-      if (lane == 0) ws.P[kk] = j;
-      kk++;
-    }
+    // factor the inherited set (ascending column order); x outside the set is zero
     _Pragma("unroll 1") for (int j = lane; j < n; j += 32)
-      if (!((mask >> j) & 1ull)) ws.x[j] = 0.0;
+      if ((mask >> j) & 1ull) {
+        P[__popcll(mask & ((1ull << j) - 1ull))] = j;
+      } else {
+        V[GV_X + j] = 0.0;
+      }
     __syncwarp();
-    k = kk;
-    gram_rebuild(p, ws, k, 0);
-    if (k != kk) mask = mask_of(ws.P, k);  // a column was dropped as dependent
-    need_solve_check = (k > 0);
+    const int kk = __popcll(mask);
+    k = gram_refactor(V, ld, kk, mu2);
+    if (k != kk) mask = mask_of(P, k);  // a column was dropped as dependent
+    check_first = (k > 0);
     if (k == 0) {
-      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) ws.w[j] = p.c[j];
+      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) V[GV_W + j] = V[GV_C + j];
       __syncwarp();
     }
   }
 
-  bool terminated = false;
   while (true) {
-    if (!need_solve_check) {
-      if (k >= p.max_set) break;
+    if (!check_first) {
+      if (k >= max_set) break;
       // ---- entering column: largest positive dual, first on ties; test its coefficient ----
-      bool accepted = false;
-      while (true) {
-        double best = 0.0;
-        int bj = 0x7fffffff;
-        _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
-          double v = ws.w[j];
-          if (!((mask >> j) & 1ull) && v > best) best = v, bj = j;
-        }
-        warp_argmax_first(best, bj);
-        if (!(best > 0.0)) {
-          terminated = true;
-          break;
-        }
-        if (gram_append(p, ws, k, bj, true)) {
-          mask |= 1ull << bj;
-          accepted = true;
-          break;
-        }
-        if (lane == 0) ws.w[bj] = 0.0;  // rejected (src/NNLS.jl:652-657)
-        __syncwarp();
+      unsigned long long key = 0ull, best;
+      int bj = 0x7fffffff;
+      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
+        const double v = V[GV_W + j];
+        const unsigned long long kb = (unsigned long long)__double_as_longlong(v);
+        if (!((mask >> j) & 1ull) && v > 0.0 && kb > key) key = kb, bj = j;
       }
-      if (terminated || !accepted) break;
+      bj = warp_argmax_bits(key, bj, best);
+      if (best == 0ull) break;  // no positive dual left: KKT point
+      if (!gram_append(V, ld, k, bj, mu2, true)) {
+        if (lane == 0) V[GV_W + bj] = 0.0;  // rejected (src/NNLS.jl:652-657)
+        __syncwarp();
+        continue;
+      }
+      k += 1;
+      mask |= 1ull << bj;
     }
-    need_solve_check = false;
+    check_first = false;
 
     // ---- secondary loop: keep the iterate feasible (src/NNLS.jl:692-786) ----
+    bool capped = false;
     while (true) {
       iter += 1;
       if (iter > max_iter) {
-        terminated = true;
+        capped = true;
         break;
       }
-      double al = 2.0;
+      unsigned long long key = ~0ull, best;
       int imv = 0x7fffffff;
       _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
-        double st = ws.s[t];
+        const double st = V[GV_S + t];
         if (st <= 0.0) {
-          double xi = ws.x[ws.P[t]];
-          double tt = ddiv(-xi, st - xi);
-          if (al > tt) al = tt, imv = t;
+          const double xi = V[GV_X + P[t]];
+          const double tt = ddiv(-xi, st - xi);
+          const unsigned long long kb = (unsigned long long)__double_as_longlong(tt);
+          if (tt < 2.0 && kb < key) key = kb, imv = t;  // tt >= 0 here, so the bit pattern orders like the value
         }
       }
-      warp_argmin_first(al, imv);
-      if (!(al < 2.0)) break;  // all coefficients feasible
+      if (__all_sync(DECAES_FULL_MASK, key == ~0ull)) break;  // all coefficients feasible
+      imv = warp_argmin_bits(key, imv, best);
+      const double al = __longlong_as_double((long long)best);
       _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
-        int jx = ws.P[t];
-        ws.x[jx] = fma(al, ws.s[t] - ws.x[jx], ws.x[jx]);
+        const int jx = P[t];
+        V[GV_X + jx] = fma(al, V[GV_S + t] - V[GV_X + jx], V[GV_X + jx]);
       }
       __syncwarp();
       // remove imv, then any other non-positive coefficient (first found), compacting P
-      int first_removed = imv;
       while (true) {
         if (lane == 0) {
-          int jr = ws.P[imv];
-          ws.x[jr] = 0.0;
-          for (int t = imv; t < k - 1; t++) ws.P[t] = ws.P[t + 1];
+          V[GV_X + P[imv]] = 0.0;
+          for (int t = imv; t < k - 1; t++) P[t] = P[t + 1];
         }
         __syncwarp();
         k -= 1;
-        if (imv < first_removed) first_removed = imv;
-        unsigned bad0 = __ballot_sync(DECAES_FULL_MASK, lane < k && ws.x[ws.P[lane]] <= 0.0);
-        unsigned bad1 = __ballot_sync(DECAES_FULL_MASK, lane + 32 < k && ws.x[ws.P[lane + 32]] <= 0.0);
-        if (bad0) imv = __ffs(bad0) - 1;
-        else if (bad1) imv = 32 + __ffs(bad1) - 1;
-        else break;
+        unsigned bad = 0x7fffffffu;
+        _Pragma("unroll 1") for (int t = lane; t < k; t += 32)
+          if (V[GV_X + P[t]] <= 0.0 && (unsigned)t < bad) bad = t;
+        bad = __reduce_min_sync(DECAES_FULL_MASK, bad);
+        if (bad == 0x7fffffffu) break;
+        imv = (int)bad;
       }
-      gram_rebuild(p, ws, k, first_removed);
-      mask = mask_of(ws.P, k);
+      k = gram_refactor(V, ld, k, mu2);
+      mask = mask_of(P, k);
     }
-    if (terminated) break;
+    if (capped) break;
 
-    _Pragma("unroll 1") for (int t = lane; t < k; t += 32) ws.x[ws.P[t]] = ws.s[t];
+    _Pragma("unroll 1") for (int t = lane; t < k; t += 32) V[GV_X + P[t]] = V[GV_S + t];
     __syncwarp();
-    gram_dual(p, ws, k, mask);
+    // ---- dual: w_j = c_j - sum_t G(P[t], j) s_t, zero on the active set ----
+    {
+      GP_BEGIN();
+      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
+        double a = V[GV_C + j];
+        _Pragma("unroll 4") for (int t = 0; t < k; t++) a = fma(-gram_G(T, ld, P[t], j), V[GV_S + t], a);
+        V[GV_W + j] = ((mask >> j) & 1ull) ? 0.0 : a;
+      }
+      __syncwarp();
+      GP_END(2);
+    }
   }
 
   GramOut o;
   o.k = k;
   o.mask = mask;
   double acc = 0.0;
-  _Pragma("unroll 1") for (int j = lane; j < n; j += 32) acc = fma(ws.x[j], ws.x[j], acc);
+  _Pragma("unroll 1") for (int j = lane; j < n; j += 32) acc = fma(V[GV_X + j], V[GV_X + j], acc);
   o.xnorm_sq = warp_sum(acc);
+  GP_ADD(13, k);
+  GP_ADD(14, iter);
+  GP_END(3);
   return o;
 }
 

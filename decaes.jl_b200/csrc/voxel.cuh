@@ -39,6 +39,7 @@ struct PipeParams {
   int warps_per_cta, smem_per_warp;  // CTA shape: bytes of dynamic shared memory owned by each warp
   int fa_warm;              // warm-start flip-angle probes from the nearest probed angle (Gram solver)
   int sync_mask;            // which intra-round CTA barriers are active (bit 0: after flip angle, bit 1: after basis)
+  int epg_smem;             // EPG at the fitted angle keeps its states in shared memory (lane <-> component)
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
   double angles[DECAES_MAX_ANGLES];                            // flip-angle grid (degrees)
   double logT2[DECAES_MAX_NT2], E2[DECAES_MAX_NT2];            // log(T2_j), exp(-(TE/2)/T2_j)
@@ -58,7 +59,7 @@ struct ScratchLayout {
     pristine_cm = o, o += nTE * nT2 + (nTE * nT2 & 1);
     slots_x = o, o += DECAES_NCACHE * nT2;
     lc_pts = o, o += DECAES_LC_MAX * 4;
-    lc_states = o, o += DECAES_LC_MAX * 6;
+    lc_states = o, o += DECAES_LC_MAX * 5;
     fa_u = o, o += DECAES_MAX_ANGLES;
     fa_du = o, o += DECAES_MAX_ANGLES;
     fa_mask = o, o += DECAES_MAX_ANGLES;
@@ -74,38 +75,40 @@ struct SmemLayout {
   int M, c, y, s, t1, t2, lc_pts, lc_states, slots_x, fa_u, fa_du, fa_mask;  // Gram solver only
   __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems, int gram) {
     int o = 0;
-    A = o, o += a_elems;  // QR: working matrix / EPG scratch.  Gram: combined G / M array (nT2 x ldg)
     b = u = M = c = y = s = t1 = t2 = lc_pts = lc_states = slots_x = fa_u = fa_du = fa_mask = 0;
     if (gram) {
-      M = 0;  // M lives in the strictly-upper part of the G array (gram.cuh)
-      c = o, o += nT2;
-      y = o, o += nT2;
-      s = o, o += nT2;
-      t1 = o, o += nT2;
-      t2 = o, o += nT2;
+      // solver block first (gram.cuh: vectors at fixed offsets from V, then the combined G / M array)
+      c = GV_C, y = GV_Y, s = GV_S, t1 = GV_T1, t2 = GV_T2, x = GV_X, w = GV_W, idx = GV_P;
+      A = GV_T, o = GV_T + a_elems;
       lc_pts = o, o += 4 * DECAES_LC_MAX;
-      lc_states = o, o += 6 * DECAES_LC_MAX;
+      lc_states = o, o += 5 * DECAES_LC_MAX;
       slots_x = o, o += DECAES_NCACHE * nT2;
-      fa_u = o, o += DECAES_MAX_ANGLES;
-      fa_du = o, o += DECAES_MAX_ANGLES;
-      fa_mask = o, o += DECAES_MAX_ANGLES;
+      // the flip-angle tables are dead once the angle is fitted: they alias the L-curve caches
+      fa_u = lc_pts, fa_du = lc_pts + DECAES_MAX_ANGLES, fa_mask = lc_pts + 2 * DECAES_MAX_ANGLES;
+      static_assert(3 * DECAES_MAX_ANGLES <= 9 * DECAES_LC_MAX, "flip-angle tables must fit in the L-curve caches");
     } else {
+      A = o, o += a_elems;  // working matrix / EPG scratch
       b = o, o += rows_alloc;
       u = o, o += rows_alloc;
+      x = o, o += nT2;
+      w = o, o += nT2;
     }
-    x = o, o += nT2;
-    w = o, o += nT2;
     bd = o, o += nTE;
-    sig = o, o += DECAES_GROUP * nTE;
+    sig = 0;
     fit = o, o += nTE;
     slot_mu = o, o += DECAES_NCACHE;
     slot_r2 = o, o += DECAES_NCACHE;
     slot_x2 = o, o += DECAES_NCACHE;
     slot_mask = o, o += DECAES_NCACHE;
     bar = o, o += 2;
-    idx = o, o += (nT2 + 1) / 2;
+    if (!gram) idx = o, o += (nT2 + 1) / 2;
     total_bytes = ((o * 8) + 15) & ~15;
   }
+};
+
+struct GramWs {  // views into the solver block of one warp (gram.cuh layout)
+  double *y, *s, *x, *w, *t1, *t2;
+  int *P;
 };
 
 struct Src {               // where the current basis of the Gram solver lives
@@ -132,6 +135,7 @@ struct Warp {
   const PipeParams &P;
   NnlsWs ws;
   GramWs gws;                    // Gram solver scratch
+  double *V;                     // base of the Gram solver block in shared memory (gram.cuh layout)
   double *Gs, *cvec;             // per-voxel G = A'A and c = A'b in shared memory (Gram solver)
   unsigned long long *slot_mask; // active set of each cache slot
   // small control tables: shared memory for the Gram solver (an L2 round trip per access would
@@ -154,7 +158,7 @@ struct Warp {
     ws.A = smem + L.A, ws.b = smem + L.b, ws.u = smem + L.u, ws.x = smem + L.x, ws.w = smem + L.w;
     ws.idx = (int *)(smem + L.idx);
     ws.ld = p.ld, ws.n = p.nT2, ws.m0 = p.nTE;
-    Gs = smem + L.A, cvec = smem + L.c;
+    V = smem, Gs = smem + L.A, cvec = smem + L.c;
     gws.y = smem + L.y, gws.s = smem + L.s, gws.x = smem + L.x, gws.w = smem + L.w;
     gws.t1 = smem + L.t1, gws.t2 = smem + L.t2, gws.P = (int *)(smem + L.idx);
     slot_mask = (unsigned long long *)(smem + L.slot_mask);
@@ -165,7 +169,7 @@ struct Warp {
       lc_pts_p = gscratch + sl.lc_pts, lc_states_p = gscratch + sl.lc_states, slots_x_p = gscratch + sl.slots_x;
       fa_u_p = gscratch + sl.fa_u, fa_du_p = gscratch + sl.fa_du, fa_mask_p = (unsigned long long *)(gscratch + sl.fa_mask);
     }
-    bd = smem + L.bd, sig = smem + L.sig, fit = smem + L.fit;
+    bd = smem + L.bd, sig = nullptr, fit = smem + L.fit;
     slot_mu = smem + L.slot_mu, slot_r2 = smem + L.slot_r2, slot_x2 = smem + L.slot_x2;
     bar = (uint64_t *)(smem + L.bar);
     phase = 0;
@@ -295,7 +299,8 @@ struct Warp {
   __device__ void basis_at(double alpha, long long v) {
     if constexpr (GRAM) {
       PROF_BEGIN(7);
-      if (P.nTE <= 63) epg_basis_shfl<false>(alpha, v);
+      if (P.epg_smem) epg_basis(alpha, v, V);  // lane <-> T2 component, states in the (idle) solver block
+      else if (P.nTE <= 63) epg_basis_shfl<false>(alpha, v);
       else epg_basis_shfl<true>(alpha, v);
       PROF_END(7);
       PROF_BEGIN(8);
@@ -303,7 +308,7 @@ struct Warp {
       PROF_END(8);
       cursrc.G = Gs, cursrc.ldg = P.ldg, cursrc.Arm = g + sl.pristine, cursrc.Acm = g + sl.pristine_cm;
     } else {
-      epg_basis(alpha, v);
+      epg_basis(alpha, v, ws.A);
     }
   }
 
@@ -361,11 +366,11 @@ struct Warp {
   // lane <-> T2 component; phase states of each lane's curve live in shared memory (the working
   // matrix region is free at this point), updated in place.  Arithmetic follows
   // epg_impulse_response! src/EPGdecaycurve.jl:948-1028 operation by operation.
-  __device__ __noinline__ void epg_basis(double alpha_deg, long long v) {
+  __device__ __noinline__ void epg_basis(double alpha_deg, long long v, double *S /* [3][K][32] shared scratch */) {
     const int ETL = P.nTE, n = P.nT2, ld = P.ld;
-    double *S = ws.A;  // [3][K][32]
     const int K = P.epg_kmax;
     double *pr = g + sl.pristine;
+    double *pc = GRAM ? g + sl.pristine_cm : nullptr;
     double sina, cosa;
     sincos(alpha_deg * 0.017453292519943295, &sina, &cosa);
     const double m0 = sind_0_180(alpha_deg / 2);
@@ -386,7 +391,11 @@ struct Warp {
   vF = fma(c, Z, __dadd_rn(Cp, Sp));            \
   vZ = fma(cp, Sd, __dmul_rn(d, Z))
       double dc = __dsub_rn(a, b);
-      if (act) pr[0 * ld + j] = fabs(__dmul_rn(m0, dc));
+      if (act) {
+        const double val = fabs(__dmul_rn(m0, dc));
+        pr[0 * ld + j] = val;
+        if (GRAM) pc[j * ETL] = val;
+      }
       ST(0, 1) = __dsub_rn(a, b), ST(1, 1) = 0.0, ST(2, 1) = cp;
       ST(0, 2) = __dadd_rn(a, b), ST(1, 2) = 0.0, ST(2, 2) = 0.0;
       for (int i = 2; i <= ETL - 1; i++) {
@@ -394,7 +403,11 @@ struct Warp {
         const int kmax = first_half ? i : ETL - i + 1;
         F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
         UPD();
-        if (act) pr[(i - 1) * ld + j] = fabs(__dmul_rn(m0, vFb));
+        if (act) {
+          const double val = fabs(__dmul_rn(m0, vFb));
+          pr[(i - 1) * ld + j] = val;
+          if (GRAM) pc[j * ETL + i - 1] = val;
+        }
         ST(0, 1) = vFb, ST(2, 1) = vZ;
         double pend = vF;
         for (int k = 2; k <= kmax; k++) {
@@ -411,7 +424,11 @@ struct Warp {
       F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
       C = __dadd_rn(F, Fb), Sd = __dsub_rn(F, Fb);
       dc = fma(-c, Z, fma(a, C, __dmul_rn(-b, Sd)));
-      if (act) pr[(ETL - 1) * ld + j] = fabs(__dmul_rn(m0, dc));
+      if (act) {
+        const double val = fabs(__dmul_rn(m0, dc));
+        pr[(ETL - 1) * ld + j] = val;
+        if (GRAM) pc[j * ETL + ETL - 1] = val;
+      }
     }
 #undef ST
 #undef UPD
@@ -605,7 +622,7 @@ struct Warp {
     double bw = CUDART_INF;
     int bk = -1;
     for (int k = lane; k < nst; k += 32) {
-      const double *s = sts + 6 * k;
+      const double *s = sts + 5 * k;
       if (s[1] == xb || s[2] == xb) {
         double w = fabs(s[3] - s[0]);
         if (w <= bw) bw = w, bk = k;
@@ -643,7 +660,7 @@ struct Warp {
         double xb = pts[4 * lc_argmax(npts)];
         int kb = lc_backtrack(xb, fabs(sx[3] - sx[0]), nst);
         if (kb >= 0) {
-          const double *s = sts + 6 * kb;
+          const double *s = sts + 5 * kb;
           unsigned long long packed = (unsigned long long)__double_as_longlong(s[4]);
           for (int q = 0; q < 4; q++) sx[q] = s[q], si[q] = (int)((packed >> (16 * q)) & 0xffff);
         }
@@ -665,11 +682,10 @@ struct Warp {
       lc_update_curvature(sx, si, npts, tlx, tly, brx, bry, Ctol);
       if (nst < DECAES_LC_MAX) {
         if (lane == 0) {
-          double *s = sts + 6 * nst;
+          double *s = sts + 5 * nst;
           unsigned long long packed = 0ull;
           for (int q = 0; q < 4; q++) s[q] = sx[q], packed |= ((unsigned long long)si[q]) << (16 * q);
           s[4] = __longlong_as_double((long long)packed);
-          s[5] = (double)iter;
         }
         nst++;
         __syncwarp();
@@ -1000,20 +1016,14 @@ struct Warp {
   // `warm_mask` != 0: start from that active set instead (flip-angle probes only: the loss and its
   // gradient depend on the minimiser, which is unique, not on the pivoting path).
   __device__ __noinline__ double gram_solve_unreg(const Src &src, GramOut &o, unsigned long long warm_mask = 0ull) {
-    GramProb pr;
-    pr.T = Gs, pr.ld = P.ldg, pr.c = cvec, pr.mu2 = 0.0, pr.n = P.nT2;
-    pr.max_set = P.nTE < P.nT2 ? P.nTE : P.nT2;
+    const int max_set = P.nTE < P.nT2 ? P.nTE : P.nT2;
     if (warm_mask) {
       _Pragma("unroll 1") for (int j = lane; j < P.nT2; j += 32) gws.x[j] = ((warm_mask >> j) & 1ull) ? 1.0 : 0.0;
       __syncwarp();
-      PROF_BEGIN(1);
-      o = gram_nnls(pr, gws, true, warm_mask);
-      PROF_END(1);
-    } else {
-      PROF_BEGIN(1);
-      o = gram_nnls(pr, gws, false, 0ull);
-      PROF_END(1);
     }
+    PROF_BEGIN(1);
+    o = gram_nnls(V, P.nT2, P.ldg, 0.0, max_set, warm_mask != 0ull, warm_mask);
+    PROF_END(1);
     PROF_BEGIN(2);
     double r2 = gram_residual(src.Acm, o.k);
     PROF_END(2);
@@ -1194,28 +1204,23 @@ struct Warp {
       return;
     }
     cur_slot = (firstnan >= 0) ? firstnan : (cur_slot + 1) % DECAES_NCACHE;
-    GramProb pr;
-    pr.T = Gs, pr.ld = P.ldg, pr.c = cvec, pr.mu2 = __dmul_rn(mu, mu), pr.n = n, pr.max_set = n;
+    const double mu2 = __dmul_rn(mu, mu);
     GramOut o;
     if (nearest >= 0) {
       const double *sx = slots_x_p + nearest * n;
       _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = sx[j];
       __syncwarp();
-      PROF_BEGIN(9);
-      o = gram_nnls(pr, gws, true, slot_mask[nearest]);
-      PROF_END(9);
-    } else {
-      PROF_BEGIN(9);
-      o = gram_nnls(pr, gws, false, 0ull);
-      PROF_END(9);
     }
+    PROF_BEGIN(9);
+    o = gram_nnls(V, n, P.ldg, mu2, n, nearest >= 0, nearest >= 0 ? slot_mask[nearest] : 0ull);
+    PROF_END(9);
     PROF_BEGIN(2);
     double r2 = gram_residual(src.Acm, o.k);
     PROF_END(2);
     if (o.k > 0 && P.refine_tikh) {
       // one refinement step on the explicit residual: x(mu) accurate to ~cond([A; mu I]) * eps, so
       // that ||Ax - b||^2 and ||x||^2 (the inputs of the mu searches) carry reference-level noise
-      gram_refine(src.Acm, o.k, pr.mu2);
+      gram_refine(src.Acm, o.k, mu2);
       r2 = gram_residual(src.Acm, o.k);
       double acc = 0.0;
       for (int t = lane; t < o.k; t += 32) acc = fma(gws.s[t], gws.s[t], acc);
@@ -1236,17 +1241,19 @@ struct Warp {
   double max_signal_cur, alpha_cur;
 
   // phase 1: normalise (src/T2mapSEcorr.jl:205-218) and fit the flip angle (:409-423)
-  __device__ __noinline__ void phase_flip_angle(long long v, const double *signal /* smem, nTE */) {
+  __device__ __noinline__ void phase_flip_angle(long long v, const double *signal /* global: image + v, echo stride P.stride */) {
     const int nTE = P.nTE;
     v_cur = v;
     double mx = 0.0;
     for (int i = lane; i < nTE; i += 32) {
-      double bi = signal[i];
+      double bi = __ldg(signal + (long long)i * P.stride);
+      bd[i] = bi;
       mx = bi > mx ? bi : mx;
     }
     const double max_signal = warp_max(mx);
     max_signal_cur = max_signal;
-    for (int i = lane; i < nTE; i += 32) bd[i] = (max_signal > 0) ? signal[i] / max_signal : signal[i];
+    if (max_signal > 0)
+      for (int i = lane; i < nTE; i += 32) bd[i] = bd[i] / max_signal;
     __syncwarp();
     if (P.alpha_provided) alpha_cur = P.alpha[v];
     else if (P.fixed_alpha) alpha_cur = P.SetFlipAngle;
