@@ -267,6 +267,7 @@ def main():
                        "voxels_per_rank": nvox, "l2": "inputs+outputs per step exceed L2 (no flush needed)",
                        "debug_voxels_override": bool(args.voxels)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps,
+            "kernel_ms_per_step": sum(kernel_ms) / max(len(kernel_ms), 1),
             "roofline": roofline, "cpu_baseline": cpu,
             "voxels_processed_last_step": processed, "checksum_gdn": checksum,
         }

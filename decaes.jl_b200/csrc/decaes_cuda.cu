@@ -682,8 +682,16 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
     fprintf(stderr, "  mean k at append %.1f, at factor %.1f; nnls warm %.1f cold %.1f per voxel, mean final k %.1f, mean inner iters %.2f, factor fallbacks/voxel %.3f\n",
             gp[4] ? (double)gp[8] / gp[4] : 0.0, gp[5] ? (double)gp[9] / gp[5] : 0.0, gp[11] / nv, gp[12] / nv,
             gp[7] ? (double)gp[13] / gp[7] : 0.0, gp[7] ? (double)gp[14] / gp[7] : 0.0, gp[15] / nv);
+    unsigned long long kh[10];
+    cudaMemcpyFromSymbol(kh, g_khist, sizeof kh);
+    for (int w = 0; w < 2; w++)
+      fprintf(stderr, "  k at %s: <=4 %.1f%%  <=8 %.1f%%  <=12 %.1f%%  <=16 %.1f%%  >16 %.1f%%\n", w ? "factor" : "append",
+              100.0 * kh[5 * w] / std::max<double>(1, (double)gp[4 + w]), 100.0 * kh[5 * w + 1] / std::max<double>(1, (double)gp[4 + w]),
+              100.0 * kh[5 * w + 2] / std::max<double>(1, (double)gp[4 + w]), 100.0 * kh[5 * w + 3] / std::max<double>(1, (double)gp[4 + w]),
+              100.0 * kh[5 * w + 4] / std::max<double>(1, (double)gp[4 + w]));
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(g_prof, z, sizeof z);
+    cudaMemcpyToSymbol(g_khist, z, sizeof kh);
   }
 #endif
   st->kernel_launches += 3;

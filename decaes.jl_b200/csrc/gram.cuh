@@ -37,10 +37,13 @@ namespace decaes {
 // [0..3] cycles append/factor/dual/nnls, [4..7] calls, [8] sum k at append, [9] sum k at factor,
 // [11] warm calls, [12] cold calls, [13] sum final k, [14] sum inner iterations, [15] factor fallbacks
 __device__ unsigned long long g_prof[16];
+__device__ unsigned long long g_khist[2][5];  // k at append / factor: <=4, <=8, <=12, <=16, >16
 #define GP_BEGIN() long long gp_t0 = clock64()
 #define GP_END(id) if (lane_id() == 0) { atomicAdd(&g_prof[id], (unsigned long long)(clock64() - gp_t0)); atomicAdd(&g_prof[4 + id], 1ull); }
 #define GP_ADD(id, v) if (lane_id() == 0) atomicAdd(&g_prof[id], (unsigned long long)(v))
+#define GP_HIST(w, k) if (lane_id() == 0) atomicAdd(&g_khist[w][(k) <= 4 ? 0 : (k) <= 8 ? 1 : (k) <= 12 ? 2 : (k) <= 16 ? 3 : 4], 1ull)
 #else
+#define GP_HIST(w, k)
 #define GP_BEGIN()
 #define GP_END(id)
 #define GP_ADD(id, v)
@@ -98,6 +101,7 @@ __device__ __noinline__ bool gram_append(double *V, int ld, int k, int j, double
   const int *P = (const int *)(V + GV_P);
   GP_BEGIN();
   GP_ADD(8, k);
+  GP_HIST(0, k);
   _Pragma("unroll 1") for (int t = lane; t < k; t += 32) V[GV_T1 + t] = gram_G(T, ld, P[t], j);
   __syncwarp();
   // l = M g  (lane <-> row t; for fixed u the lanes read consecutive words)
@@ -144,72 +148,61 @@ __device__ __noinline__ bool gram_append(double *V, int ld, int k, int j, double
 }
 
 // Factor the whole active block at once: M = L^-1 with G_PP + mu2 I = L L', y = M c_P, s = M'y for
-// the k columns listed in P.  Symmetric Gaussian elimination on [K | c | I], lane <-> row, done in
-// place in M's storage: after step p, row i holds the multipliers R(i, 0..p) of the unit lower
-// triangular R = Ltilde^-1 and the still-to-be-eliminated K entries (i, p+1..i).  M = D^-1/2 R.
+// the k columns listed in P.  Symmetric Gaussian elimination on [K | c | I] done in place in M's
+// storage: after step p, row i holds the multipliers R(i, 0..p) of the unit lower triangular
+// R = Ltilde^-1 and the still-to-be-eliminated K entries (i, p+1..i).  M = D^-1/2 R.
+// Work split: lane -> (row i = lane / 4 + 8a, entries q = lane % 4 + 4e), so that the usual block
+// (k <= 8) takes one row and at most two entries per lane and the loops below run once or twice.
+// (A register-resident, fully unrolled variant is 2-3x faster in isolation and SLOWER inside the
+// pipeline: the kernel is instruction-fetch bound and straight-line code has no reuse.)
 // Returns false when a pivot is not positive (numerically dependent set): the caller falls back
 // to sequential appends, which drop the offending column.
 __device__ __noinline__ bool gram_factor(double *V, int ld, int k, double mu2) {
   __builtin_assume(__isShared(V));
   const int lane = lane_id();
+  const int r0 = lane >> 2, c0 = lane & 3;
   double *T = V + GV_T;
   const int *P = (const int *)(V + GV_P);
   GP_BEGIN();
   GP_ADD(9, k);
-  _Pragma("unroll 1") for (int i = lane; i < k; i += 32) {
+  GP_HIST(1, k);
+  _Pragma("unroll 1") for (int i = r0; i < k; i += 8) {
     const int pi = P[i];
-    _Pragma("unroll 1") for (int q0 = 0; q0 < i; q0 += 4) {  // four gathers in flight
-      double g[4];
-      _Pragma("unroll") for (int e = 0; e < 4; e++) g[e] = gram_G(T, ld, pi, P[q0 + e < i ? q0 + e : i]);
-      _Pragma("unroll") for (int e = 0; e < 4; e++)
-        if (q0 + e < i) GM_(i, q0 + e) = g[e];
-    }
-    GM_(i, i) = T[pi * ld + pi] + mu2;
-    V[GV_Y + i] = V[GV_C + pi];
+    _Pragma("unroll 1") for (int q = c0; q <= i; q += 4) GM_(i, q) = gram_G(T, ld, pi, P[q]) + (q == i ? mu2 : 0.0);
+    if (c0 == 0) V[GV_Y + i] = V[GV_C + pi];
   }
   bool ok = true;
   _Pragma("unroll 1") for (int p = 0; p < k; p++) {
-    // snapshot of column p (rows >= p), double-buffered in t1 / t2 so one barrier per step suffices;
-    // every row stays with the same lane throughout
+    __syncwarp();
+    // snapshot of column p (rows >= p), double-buffered in t1 / t2 so one barrier per step suffices
     double *col = V + ((p & 1) ? GV_T2 : GV_T1);
-    _Pragma("unroll 1") for (int i = lane; i < k; i += 32)
-      if (i >= p) col[i] = GM_(i, p);
+    _Pragma("unroll 1") for (int i = p + lane; i < k; i += 32) col[i] = GM_(i, p);
     __syncwarp();
     const double d = col[p];
     if (!(d > 0.0)) {
       ok = false;
       break;
     }
-    const double rinv = __drcp_rn(d), yp = V[GV_Y + p];
-    _Pragma("unroll 1") for (int i = lane; i < k; i += 32) {
+    const double rinv = __drcp_rn(d);
+    _Pragma("unroll 1") for (int i = r0; i < k; i += 8) {
       if (i <= p) continue;
       const double f = col[i] * rinv;
-      // row_i -= f * (row p of R | column p of K), entries q in [0, i] \ {p}; four at a time so the
-      // loads of a batch are in flight together (the compiler cannot reorder them across the stores)
-      _Pragma("unroll 1") for (int q0 = 0; q0 <= i; q0 += 4) {
-        double a[4], o[4];
-        _Pragma("unroll") for (int e = 0; e < 4; e++) {
-          const int q = q0 + e;
-          const int qq = (q <= i && q != p) ? q : i;
-          a[e] = GM_(i, qq);
-          o[e] = (qq < p) ? GM_(p, qq) : col[qq];
-        }
-        _Pragma("unroll") for (int e = 0; e < 4; e++) {
-          const int q = q0 + e;
-          if (q <= i && q != p) GM_(i, q) = fma(-f, o[e], a[e]);
-        }
+      // row_i -= f * (row p of R | column p of K) on the entries q in [0, i] \ {p}; entry p becomes -f
+      _Pragma("unroll 1") for (int q = c0; q <= i; q += 4) {
+        const double o = (q < p) ? GM_(p, q) : col[q];
+        GM_(i, q) = (q == p) ? -f : fma(-f, o, GM_(i, q));
       }
-      GM_(i, p) = -f;
-      V[GV_Y + i] = fma(-f, yp, V[GV_Y + i]);
+      if (c0 == 0) V[GV_Y + i] = fma(-f, V[GV_Y + p], V[GV_Y + i]);
     }
   }
   __syncwarp();
   if (ok) {
-    _Pragma("unroll 1") for (int i = lane; i < k; i += 32) {
+    _Pragma("unroll 1") for (int i = r0; i < k; i += 8) {
       const double dinv = rsqrt(GM_(i, i));
-      _Pragma("unroll 4") for (int q = 0; q < i; q++) GM_(i, q) *= dinv;
-      GM_(i, i) = dinv;
-      V[GV_Y + i] *= dinv;
+      __syncwarp(0xfu << (lane & 28));  // the four lanes of a row read the pivot before it is overwritten
+      _Pragma("unroll 1") for (int q = c0; q < i; q += 4) GM_(i, q) *= dinv;
+      if (c0 == (i & 3)) GM_(i, i) = dinv;
+      if (c0 == 0) V[GV_Y + i] *= dinv;
     }
     __syncwarp();
     _Pragma("unroll 1") for (int u = lane; u < k; u += 32) {

@@ -5,6 +5,6 @@ import sys,json
 t=''
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print('value', round(d['value']), 'clk', d['clocks']['sm_mhz'], t)
+        d=json.loads(l); print('value', round(d['value']), 'ms', round(d['ms_per_step'],1), 'kern_ms', round(d['kernel_ms_per_step'],1), t)
     elif 'warp-cycles' in l: t=l.strip().split('voxel:')[-1]
 "; done; done
