@@ -91,6 +91,13 @@ __device__ __forceinline__ int warp_argmin_bits(unsigned long long key, int idx,
   return (int)__reduce_min_sync(DECAES_FULL_MASK, (key == best) ? (unsigned)idx : 0x7fffffffu);
 }
 
+// Order-preserving map double -> uint64 (total order -inf < ... < -0 < +0 < ... < +inf; NaNs are the
+// caller's business), so that value reductions can run on the integer REDUX unit.
+__device__ __forceinline__ unsigned long long dkey(double x) {
+  const long long b = __double_as_longlong(x);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+
 // Append column j to the factorisation at pivot position k.  Returns false (and changes nothing)
 // when the column is numerically dependent (d^2 <= 0) or, with `need_positive`, when its
 // coefficient would not be positive (the reference's b1/A1 > 0 test).  The caller increments k.

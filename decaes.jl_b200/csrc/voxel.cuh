@@ -538,12 +538,7 @@ struct Warp {
         found = i;
         break;
       }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      int other = __shfl_xor_sync(DECAES_FULL_MASK, found, o);
-      found = other < found ? other : found;
-    }
-    return found;
+    return (int)__reduce_min_sync(DECAES_FULL_MASK, (unsigned)found);
   }
 
   // cached evaluation of P(t) = (log ||Ax-b||^2, log ||x||^2); returns the point-cache index
@@ -568,21 +563,24 @@ struct Warp {
   __device__ __noinline__ void lc_update_curvature(const double *sx, const int *si, int npts, double tlx, double tly, double brx,
                                       double bry, double Ctol) {
     double *pts = lc_pts_p;
-    for (int q = 0; q < 4; q++) {
+    _Pragma("unroll 1") for (int q = 0; q < 4; q++) {
       int pi = si[q];
       double x = sx[q], px = pts[4 * pi + 1], py = pts[4 * pi + 2];
       double C = -CUDART_INF;
       if (fmin(norm2(px, py, tlx, tly), norm2(px, py, brx, bry)) > Ctol) {
-        // nearest cached abscissae on either side of x (src/lsqnonneg.jl:954-959)
-        double xm = -CUDART_INF, xp = CUDART_INF;
+        // nearest cached abscissae on either side of x (src/lsqnonneg.jl:954-959): first index on ties
+        unsigned long long km = 0ull, kp = ~0ull, best;
         int im = 0x7fffffff, ip = 0x7fffffff;
-        for (int k = lane; k < npts; k += 32) {
-          double _x = pts[4 * k];
-          if (xm < _x && _x < x) xm = _x, im = k;
-          if (x < _x && _x < xp) xp = _x, ip = k;
+        _Pragma("unroll 1") for (int k = lane; k < npts; k += 32) {
+          const double _x = pts[4 * k];
+          const unsigned long long kk = dkey(_x);
+          if (_x < x && kk > km) km = kk, im = k;
+          if (x < _x && kk < kp) kp = kk, ip = k;
         }
-        warp_argmax_first(xm, im);
-        warp_argmin_first(xp, ip);
+        im = warp_argmax_bits(km, im, best);
+        if (best == 0ull) im = 0x7fffffff;
+        ip = warp_argmin_bits(kp, ip, best);
+        if (best == ~0ull) ip = 0x7fffffff;
         double mx = px, my = py, qx = px, qy = py;
         if (im != 0x7fffffff) mx = pts[4 * im + 1], my = pts[4 * im + 2];
         if (ip != 0x7fffffff) qx = pts[4 * ip + 1], qy = pts[4 * ip + 2];
@@ -597,21 +595,16 @@ struct Warp {
   // mapfindmax over the curvatures: first maximum under Base.isless (NaN is maximal)
   __device__ __noinline__ int lc_argmax(int npts) {
     const double *pts = lc_pts_p;
+    unsigned long long key = 0ull, best;
     int bi = 0x7fffffff;
-    double bc = 0.0;
-    for (int i = lane; i < npts; i += 32) {
-      double c = pts[4 * i + 3];
-      if (bi == 0x7fffffff || isless_f(bc, c)) bc = c, bi = i;
+    _Pragma("unroll 1") for (int i = lane; i < npts; i += 32) {
+      const double c = pts[4 * i + 3];
+      // isless order: -Inf < ... < -0 < +0 < ... < +Inf < NaN; +1 keeps "no candidate" (0) below -Inf... (dkey(-Inf) > 0 already)
+      const unsigned long long kk = isnan(c) ? ~0ull : dkey(c);
+      if (bi == 0x7fffffff || kk > key) key = kk, bi = i;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double oc = __shfl_xor_sync(DECAES_FULL_MASK, bc, o);
-      int oi = __shfl_xor_sync(DECAES_FULL_MASK, bi, o);
-      bool take = (oi != 0x7fffffff) &&
-                  (bi == 0x7fffffff || isless_f(bc, oc) || (!isless_f(oc, bc) && oi < bi));
-      if (take) bc = oc, bi = oi;
-    }
-    return __shfl_sync(DECAES_FULL_MASK, bi, 0);
+    if (bi == 0x7fffffff) key = 0ull;
+    return warp_argmax_bits(key, bi, best);
   }
 
   // backtracking (src/lsqnonneg.jl:892-900): among the stored states that have the arg-max point as
@@ -619,24 +612,20 @@ struct Warp {
   // does not exceed the current state's.  Returns its index or -1.
   __device__ __noinline__ int lc_backtrack(double xb, double wcur, int nst) {
     const double *sts = lc_states_p;
-    double bw = CUDART_INF;
+    unsigned long long key = ~0ull;  // widths are >= 0: their bit patterns order like the values
     int bk = -1;
-    for (int k = lane; k < nst; k += 32) {
+    _Pragma("unroll 1") for (int k = lane; k < nst; k += 32) {
       const double *s = sts + 5 * k;
       if (s[1] == xb || s[2] == xb) {
-        double w = fabs(s[3] - s[0]);
-        if (w <= bw) bw = w, bk = k;
+        const unsigned long long kk = (unsigned long long)__double_as_longlong(fabs(s[3] - s[0]));
+        if (kk <= key) key = kk, bk = k;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double ow = __shfl_xor_sync(DECAES_FULL_MASK, bw, o);
-      int ok = __shfl_xor_sync(DECAES_FULL_MASK, bk, o);
-      if (ok >= 0 && (bk < 0 || ow < bw || (ow == bw && ok > bk))) bw = ow, bk = ok;
-    }
-    bk = __shfl_sync(DECAES_FULL_MASK, bk, 0);
-    bw = __shfl_sync(DECAES_FULL_MASK, bw, 0);
-    return (bk >= 0 && bw <= wcur) ? bk : -1;
+    const unsigned hi = __reduce_min_sync(DECAES_FULL_MASK, (unsigned)(key >> 32));
+    const unsigned lo = __reduce_min_sync(DECAES_FULL_MASK, ((unsigned)(key >> 32) == hi) ? (unsigned)key : 0xffffffffu);
+    const unsigned long long best = ((unsigned long long)hi << 32) | lo;
+    bk = (int)__reduce_max_sync(DECAES_FULL_MASK, (key == best && bk >= 0) ? (unsigned)(bk + 1) : 0u) - 1;  // LAST state of minimal width
+    return (bk >= 0 && __longlong_as_double((long long)best) <= wcur) ? bk : -1;
   }
 
   __device__ __noinline__ double lcurve_corner(const double *Asrc) {
