@@ -27,7 +27,7 @@ __device__ __noinline__ double dlog(double a) { return log(a); }
 __device__ __noinline__ double dexp(double a) { return exp(a); }
 
 // Butterfly sums: every lane ends with the bitwise-identical total (addition commutes).
-__device__ __forceinline__ double warp_sum(double v) {
+__device__ __noinline__ double warp_sum(double v) {  // out of line: ~40 call sites, the kernel is instruction-fetch bound
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DECAES_FULL_MASK, v, o);
   return v;

@@ -263,7 +263,7 @@ struct Warp {
     double bestu = CUDART_INF, bestx = 0.0;
     int besto = 0x7fffffff;
     // piece t connects the t-th and (t+1)-th probed node; order -1 is the first node itself
-    for (int t = lane - 1; t < npts - 1; t += 32) {
+    _Pragma("unroll 1") for (int t = lane - 1; t < npts - 1; t += 32) {
       double x_, u_;
       if (t < 0) {
         int I0 = __ffsll((long long)seen) - 1;
@@ -271,7 +271,7 @@ struct Warp {
       } else {
         // indices of the t-th and (t+1)-th set bits
         unsigned long long msk = seen;
-        for (int s = 0; s < t; s++) msk &= msk - 1;
+        _Pragma("unroll 1") for (int s = 0; s < t; s++) msk &= msk - 1;
         int Ia = __ffsll((long long)msk) - 1;
         msk &= msk - 1;
         int Ib = __ffsll((long long)msk) - 1;
@@ -283,15 +283,12 @@ struct Warp {
       bool better = (besto == 0x7fffffff) ? (ord == 0 || u_ == u_) : (u_ < bestu);
       if (better) bestu = u_, bestx = x_, besto = ord;
     }
-    // warp reduction: smaller value wins, ties -> smaller order; NaN loses (except as the seed)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double ou = __shfl_xor_sync(DECAES_FULL_MASK, bestu, o);
-      double ox = __shfl_xor_sync(DECAES_FULL_MASK, bestx, o);
-      int oo = __shfl_xor_sync(DECAES_FULL_MASK, besto, o);
-      bool take = (oo != 0x7fffffff) && (besto == 0x7fffffff || ou < bestu || (ou == bestu && oo < besto));
-      if (take) bestu = ou, bestx = ox, besto = oo;
-    }
+    // warp reduction on the REDUX unit: smaller value wins, ties -> smaller order; NaN loses
+    const unsigned long long key = (besto == 0x7fffffff) ? ~0ull : (bestu != bestu ? ~0ull - 1ull : dkey(bestu));
+    unsigned long long best;
+    const int ord = warp_argmin_bits(key, besto, best);
+    const int winner = __ffs(__ballot_sync(DECAES_FULL_MASK, key == best && besto == ord)) - 1;
+    bestx = __shfl_sync(DECAES_FULL_MASK, bestx, winner), bestu = __shfl_sync(DECAES_FULL_MASK, bestu, winner);
     xs = warp_bcast(bestx, 0), us = warp_bcast(bestu, 0);
   }
 
@@ -924,18 +921,10 @@ struct Warp {
   __device__ __noinline__ void gram_rhs(const double *Arm) {
     const int nTE = P.nTE, ld = P.ld;
     _Pragma("unroll 1") for (int j = lane; j < P.nT2; j += 32) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       const double *col = Arm + j;
-      int i = 0;
-      // eight independent global loads in flight per lane (the matrix lives in L2)
-      _Pragma("unroll 1") for (; i + 7 < nTE; i += 8) {
-        double v0 = col[i * ld], v1 = col[(i + 1) * ld], v2 = col[(i + 2) * ld], v3 = col[(i + 3) * ld];
-        double v4 = col[(i + 4) * ld], v5 = col[(i + 5) * ld], v6 = col[(i + 6) * ld], v7 = col[(i + 7) * ld];
-        a0 = fma(v0, bd[i], a0), a1 = fma(v1, bd[i + 1], a1), a2 = fma(v2, bd[i + 2], a2), a3 = fma(v3, bd[i + 3], a3);
-        a0 = fma(v4, bd[i + 4], a0), a1 = fma(v5, bd[i + 5], a1), a2 = fma(v6, bd[i + 6], a2), a3 = fma(v7, bd[i + 7], a3);
-      }
-      _Pragma("unroll 1") for (; i < nTE; i++) a0 = fma(col[i * ld], bd[i], a0);
-      cvec[j] = (a0 + a1) + (a2 + a3);
+      double a = 0.0;
+      _Pragma("unroll 8") for (int i = 0; i < nTE; i++) a = fma(col[i * ld], bd[i], a);  // the matrix lives in L2: 8 loads in flight
+      cvec[j] = a;
     }
     __syncwarp();
   }
@@ -945,16 +934,8 @@ struct Warp {
     const int nTE = P.nTE;
     double acc = 0.0;
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
-      double a0 = bd[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int t = 0;
-      _Pragma("unroll 1") for (; t + 3 < k; t += 4) {
-        double v0 = Acm[gws.P[t] * nTE + i], v1 = Acm[gws.P[t + 1] * nTE + i];
-        double v2 = Acm[gws.P[t + 2] * nTE + i], v3 = Acm[gws.P[t + 3] * nTE + i];
-        a0 = fma(-v0, gws.s[t], a0), a1 = fma(-v1, gws.s[t + 1], a1);
-        a2 = fma(-v2, gws.s[t + 2], a2), a3 = fma(-v3, gws.s[t + 3], a3);
-      }
-      _Pragma("unroll 1") for (; t < k; t++) a0 = fma(-Acm[gws.P[t] * nTE + i], gws.s[t], a0);
-      double r = (a0 + a1) + (a2 + a3);
+      double r = bd[i];
+      _Pragma("unroll 4") for (int t = 0; t < k; t++) r = fma(-Acm[gws.P[t] * nTE + i], gws.s[t], r);
       fit[i] = r;
       acc = fma(r, r, acc);
     }
@@ -969,30 +950,37 @@ struct Warp {
     const int nTE = P.nTE;
     double *T = Gs;
     const int ld = P.ldg;
-    // g_t = A[:,P[t]]' r - mu2 s_t      (lane <-> active column)
-    _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
-      const double *col = Acm + gws.P[t] * nTE;
+    // g_t = A[:,P[t]]' r - mu2 s_t: lane <-> echo (coalesced L2 reads, all lanes busy), two columns per round
+    _Pragma("unroll 1") for (int t = 0; t < k; t += 2) {
+      const int t1c = t + 1 < k ? t + 1 : t;
+      const double *c0 = Acm + gws.P[t] * nTE, *c1 = Acm + gws.P[t1c] * nTE;
       double a0 = 0.0, a1 = 0.0;
-      int i = 0;
-      _Pragma("unroll 1") for (; i + 1 < nTE; i += 2) {
-        a0 = fma(col[i], fit[i], a0);
-        a1 = fma(col[i + 1], fit[i + 1], a1);
+      _Pragma("unroll 2") for (int i = lane; i < nTE; i += 32) {
+        const double ri = fit[i];
+        a0 = fma(c0[i], ri, a0), a1 = fma(c1[i], ri, a1);
       }
-      if (i < nTE) a0 = fma(col[i], fit[i], a0);
-      gws.t1[t] = fma(-mu2, gws.s[t], a0 + a1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(DECAES_FULL_MASK, a0, o);
+        a1 += __shfl_xor_sync(DECAES_FULL_MASK, a1, o);
+      }
+      if (lane == 0) {
+        gws.t1[t] = fma(-mu2, gws.s[t], a0);
+        if (t + 1 < k) gws.t1[t + 1] = fma(-mu2, gws.s[t + 1], a1);
+      }
     }
     __syncwarp();
     // v = M g
     _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
       double a = 0.0;
-      for (int u = 0; u <= t; u++) a = fma(GM_(t, u), gws.t1[u], a);
+      _Pragma("unroll 4") for (int u = 0; u <= t; u++) a = fma(GM_(t, u), gws.t1[u], a);
       gws.t2[t] = a;
     }
     __syncwarp();
     // s += M' v
     _Pragma("unroll 1") for (int u = lane; u < k; u += 32) {
       double a = 0.0;
-      for (int t = u; t < k; t++) a = fma(GM_(t, u), gws.t2[t], a);
+      _Pragma("unroll 4") for (int t = u; t < k; t++) a = fma(GM_(t, u), gws.t2[t], a);
       double sn = gws.s[u] + a;
       gws.s[u] = sn;
       gws.x[gws.P[u]] = sn;
@@ -1057,8 +1045,10 @@ struct Warp {
     PROF_BEGIN(4);
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
       double dax = 0.0;
-      for (int t = 0; t < o.k; t++)
-        if (gws.s[t] > 0.0) dax = fma(gws.s[t], dAk[gws.P[t] * nTE + i], dax);
+      _Pragma("unroll 4") for (int t = 0; t < o.k; t++) {
+        const double st = gws.s[t], dv = dAk[gws.P[t] * nTE + i];
+        if (st > 0.0) dax = fma(st, dv, dax);
+      }
       acc = fma(dax, -fit[i], acc);  // A x - b = -r
     }
     du = 2.0 * warp_sum(acc);
@@ -1176,7 +1166,7 @@ struct Warp {
     const int n = P.nT2;
     int hit = -1, firstnan = -1, nearest = -1;
     double dbest = CUDART_INF;
-    for (int i = 0; i < DECAES_NCACHE; i++) {
+    _Pragma("unroll 1") for (int i = 0; i < DECAES_NCACHE; i++) {
       double mui = slot_mu[i];
       if (isnan(mui)) {
         if (firstnan < 0) firstnan = i;
@@ -1212,7 +1202,7 @@ struct Warp {
       gram_refine(src.Acm, o.k, mu2);
       r2 = gram_residual(src.Acm, o.k);
       double acc = 0.0;
-      for (int t = lane; t < o.k; t += 32) acc = fma(gws.s[t], gws.s[t], acc);
+      _Pragma("unroll 1") for (int t = lane; t < o.k; t += 32) acc = fma(gws.s[t], gws.s[t], acc);
       o.xnorm_sq = warp_sum(acc);
     }
     double *sx = slots_x_p + cur_slot * n;
@@ -1234,7 +1224,7 @@ struct Warp {
     const int nTE = P.nTE;
     v_cur = v;
     double mx = 0.0;
-    for (int i = lane; i < nTE; i += 32) {
+    _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
       double bi = __ldg(signal + (long long)i * P.stride);
       bd[i] = bi;
       mx = bi > mx ? bi : mx;
@@ -1242,7 +1232,7 @@ struct Warp {
     const double max_signal = warp_max(mx);
     max_signal_cur = max_signal;
     if (max_signal > 0)
-      for (int i = lane; i < nTE; i += 32) bd[i] = bd[i] / max_signal;
+      _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) bd[i] = ddiv(bd[i], max_signal);
     __syncwarp();
     if (P.alpha_provided) alpha_cur = P.alpha[v];
     else if (P.fixed_alpha) alpha_cur = P.SetFlipAngle;
