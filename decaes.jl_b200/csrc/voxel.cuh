@@ -128,6 +128,15 @@ struct Src {               // where the current basis of the Gram solver lives
 enum { PF_RHS = 0, PF_NNLS_UNREG, PF_RESID, PF_REFINE, PF_GRAD, PF_STAGE, PF_SUGGEST, PF_EPG, PF_BUILD, PF_NNLS_TIKH,
        PF_LC_BOOK, PF_SAVE, PF_COUNT };
 
+// Member functions copy the pointers they use into locals and tell the compiler that they point to
+// shared memory: otherwise every access is a generic LD/ST, and every store forces a reload of the
+// members of *this (which lives in local memory) because it might alias them.
+#define SH(p) __builtin_assume(__isShared(p))
+#define SHG(p) do { if constexpr (GRAM) __builtin_assume(__isShared(p)); } while (0)
+#define VIEW(T, name) T *const name = this->name; SH(name)
+#define VIEWG(T, name) T *const name = this->name; SHG(name)
+#define VIEW_GWS() const GramWs gws = this->gws; SH(gws.y); SH(gws.s); SH(gws.x); SH(gws.w); SH(gws.t1); SH(gws.t2); SH(gws.P)
+
 template <bool GRAM>
 struct Warp {
   long long prof_cyc[PF_COUNT] = {0};
@@ -258,6 +267,9 @@ struct Warp {
   // suggest_point  src/splines.jl:544-566.  Pieces are evaluated in parallel (lane <-> piece);
   // "first strictly smaller wins" of the sequential scan = lexicographic min over (value, order).
   __device__ __noinline__ void suggest_point(unsigned long long seen, double &xs, double &us) {
+    const int lane = this->lane;
+    VIEWG(double, fa_u_p);
+    VIEWG(double, fa_du_p);
     const double *fu = fa_u_p, *fdu = fa_du_p;
     int npts = __popcll(seen);
     double bestu = CUDART_INF, bestx = 0.0;
@@ -364,6 +376,8 @@ struct Warp {
   // matrix region is free at this point), updated in place.  Arithmetic follows
   // epg_impulse_response! src/EPGdecaycurve.jl:948-1028 operation by operation.
   __device__ __noinline__ void epg_basis(double alpha_deg, long long v, double *S /* [3][K][32] shared scratch */) {
+    const int lane = this->lane;
+    SH(S);
     const int ETL = P.nTE, n = P.nT2, ld = P.ld;
     const int K = P.epg_kmax;
     double *pr = g + sl.pristine;
@@ -528,6 +542,8 @@ struct Warp {
 
   // first index i with isapprox(t, key_i), or INT_MAX
   __device__ __noinline__ int lc_find(double t, int npts) {
+    const int lane = this->lane;
+    VIEWG(double, lc_pts_p);
     const double *pts = lc_pts_p;
     int found = 0x7fffffff;
     for (int i = lane; i < npts; i += 32)
@@ -540,6 +556,8 @@ struct Warp {
 
   // cached evaluation of P(t) = (log ||Ax-b||^2, log ||x||^2); returns the point-cache index
   __device__ __noinline__ int lc_eval(double t, int &npts, const double *Asrc) {
+    const int lane = this->lane;
+    VIEWG(double, lc_pts_p);
     double *pts = lc_pts_p;
     int i = lc_find(t, npts);
     if (i != 0x7fffffff) return i;
@@ -559,6 +577,8 @@ struct Warp {
 
   __device__ __noinline__ void lc_update_curvature(const double *sx, const int *si, int npts, double tlx, double tly, double brx,
                                       double bry, double Ctol) {
+    const int lane = this->lane;
+    VIEWG(double, lc_pts_p);
     double *pts = lc_pts_p;
     _Pragma("unroll 1") for (int q = 0; q < 4; q++) {
       int pi = si[q];
@@ -591,6 +611,8 @@ struct Warp {
 
   // mapfindmax over the curvatures: first maximum under Base.isless (NaN is maximal)
   __device__ __noinline__ int lc_argmax(int npts) {
+    const int lane = this->lane;
+    VIEWG(double, lc_pts_p);
     const double *pts = lc_pts_p;
     unsigned long long key = 0ull, best;
     int bi = 0x7fffffff;
@@ -608,6 +630,8 @@ struct Warp {
   // an interior point, the sequential scan ends on the LAST one of minimal width, provided that width
   // does not exceed the current state's.  Returns its index or -1.
   __device__ __noinline__ int lc_backtrack(double xb, double wcur, int nst) {
+    const int lane = this->lane;
+    VIEWG(double, lc_states_p);
     const double *sts = lc_states_p;
     unsigned long long key = ~0ull;  // widths are >= 0: their bit patterns order like the values
     int bk = -1;
@@ -626,6 +650,9 @@ struct Warp {
   }
 
   __device__ __noinline__ double lcurve_corner(const double *Asrc) {
+    const int lane = this->lane;
+    VIEWG(double, lc_pts_p);
+    VIEWG(double, lc_states_p);
     const double phi = 1.618033988749895, xtol = 1e-4, Ptol = 1e-4, Ctol = 1e-4;
     double *pts = lc_pts_p, *sts = lc_states_p;
     int npts = 0, nst = 0;
@@ -919,6 +946,9 @@ struct Warp {
   // =====================================================================================
   // c = A' bd  (lane <-> column, coalesced rows of the row-major matrix)
   __device__ __noinline__ void gram_rhs(const double *Arm) {
+    const int lane = this->lane;
+    VIEW(double, bd);
+    VIEW(double, cvec);
     const int nTE = P.nTE, ld = P.ld;
     _Pragma("unroll 1") for (int j = lane; j < P.nT2; j += 32) {
       const double *col = Arm + j;
@@ -931,6 +961,10 @@ struct Warp {
 
   // explicit residual r = bd - A_P s (stored in `fit`), returns ||r||^2.  lane <-> echo.
   __device__ __noinline__ double gram_residual(const double *Acm, int k) {
+    const int lane = this->lane;
+    VIEW(double, bd);
+    VIEW(double, fit);
+    VIEW_GWS();
     const int nTE = P.nTE;
     double acc = 0.0;
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
@@ -947,6 +981,10 @@ struct Warp {
   // one step of iterative refinement on the active set: s += (G_PP + mu2 I)^-1 (A_P' r - mu2 s),
   // with r = bd - A_P s already in `fit`.  Restores QR-level accuracy of the normal-equation solve.
   __device__ __noinline__ void gram_refine(const double *Acm, int k, double mu2) {
+    const int lane = this->lane;
+    VIEW(double, fit);
+    VIEW(double, Gs);
+    VIEW_GWS();
     const int nTE = P.nTE;
     double *T = Gs;
     const int ld = P.ldg;
@@ -993,6 +1031,9 @@ struct Warp {
   // `warm_mask` != 0: start from that active set instead (flip-angle probes only: the loss and its
   // gradient depend on the minimiser, which is unique, not on the pivoting path).
   __device__ __noinline__ double gram_solve_unreg(const Src &src, GramOut &o, unsigned long long warm_mask = 0ull) {
+    const int lane = this->lane;
+    VIEW(double, V);
+    VIEW_GWS();
     const int max_set = P.nTE < P.nT2 ? P.nTE : P.nT2;
     if (warm_mask) {
       _Pragma("unroll 1") for (int j = lane; j < P.nT2; j += 32) gws.x[j] = ((warm_mask >> j) & 1ull) ? 1.0 : 0.0;
@@ -1017,6 +1058,11 @@ struct Warp {
 
   // loss_with_grad!  src/splines.jl:1010-1041 on grid angle k
   __device__ __noinline__ void fa_eval_gram(int kang, double &u, double &du, unsigned long long seen) {
+    const int lane = this->lane;
+    VIEW(double, fit);
+    VIEW(double, Gs);
+    VIEW(unsigned long long, fa_mask_p);
+    VIEW_GWS();
     const int nTE = P.nTE, n = P.nT2;
     Src src;
     src.G = P.gram_set + (size_t)kang * P.a_elems, src.ldg = P.ldg;
@@ -1139,6 +1185,8 @@ struct Warp {
   // G = A'A and c = A'bd from the row-major basis in global scratch into shared memory.
   // lane <-> column q, four rows p of G at a time.
   __device__ __noinline__ void gram_build(const double *Arm) {
+    const int lane = this->lane;
+    VIEW(double, Gs);
     const int nTE = P.nTE, n = P.nT2, ld = P.ld, ldg = P.ldg;
     for (int p0 = 0; p0 < n; p0 += 4) {
       const int qmax = (p0 + 3 < n) ? p0 + 3 : n - 1;  // only q <= p is stored
@@ -1163,6 +1211,14 @@ struct Warp {
 
   // solve!(cache, mu) for the Gram solver: exact-mu hit, else warm-start from the nearest cached mu
   __device__ __noinline__ void cache_solve_gram(double mu, const Src &src) {
+    const int lane = this->lane;
+    VIEW(double, slot_mu);
+    VIEW(double, slot_r2);
+    VIEW(double, slot_x2);
+    VIEW(unsigned long long, slot_mask);
+    VIEW(double, slots_x_p);
+    VIEW(double, V);
+    VIEW_GWS();
     const int n = P.nT2;
     int hit = -1, firstnan = -1, nearest = -1;
     double dbest = CUDART_INF;
@@ -1221,6 +1277,8 @@ struct Warp {
 
   // phase 1: normalise (src/T2mapSEcorr.jl:205-218) and fit the flip angle (:409-423)
   __device__ __noinline__ void phase_flip_angle(long long v, const double *signal /* global: image + v, echo stride P.stride */) {
+    const int lane = this->lane;
+    VIEW(double, bd);
     const int nTE = P.nTE;
     v_cur = v;
     double mx = 0.0;
@@ -1254,6 +1312,14 @@ struct Warp {
 
   // phase 3: regularised NNLS, output maps, T2part epilogue
   __device__ __noinline__ void phase_solve_and_save() {
+    const int lane = this->lane;
+    VIEW(double, bd);
+    VIEW(double, fit);
+    VIEWG(double, slots_x_p);
+    VIEWG(double, lc_pts_p);
+    const NnlsWs ws = this->ws;
+    SH(ws.x);
+    SH(ws.w);
     const int nTE = P.nTE, n = P.nT2;
     const long long v = v_cur;
     const double max_signal = max_signal_cur, alpha = alpha_cur;
