@@ -641,6 +641,7 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
   CUDA_TRY(cudaEventRecord(ws.ev[1], stream));
   int64_t ngroups = (nvox + DECAES_GROUP - 1) / DECAES_GROUP;
   int grid = (int)std::min<int64_t>(plan.grid, std::max<int64_t>((ngroups + plan.warps_per_cta - 1) / plan.warps_per_cta, 1));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(cP, &P, sizeof(PipeParams), 0, cudaMemcpyHostToDevice, stream));
   if (P.gram)
     voxel_pipeline_kernel<true><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
   else

@@ -128,6 +128,12 @@ struct Src {               // where the current basis of the Gram solver lives
 enum { PF_RHS = 0, PF_NNLS_UNREG, PF_RESID, PF_REFINE, PF_GRAD, PF_STAGE, PF_SUGGEST, PF_EPG, PF_BUILD, PF_NNLS_TIKH,
        PF_LC_BOOK, PF_SAVE, PF_COUNT };
 
+// The kernel parameters as seen by the per-warp code: a __constant__ copy (written by the host right
+// before each launch, stream-ordered), so that every field is one LDC with an immediate offset instead
+// of a pointer chase through *this.  One launch per device at a time (the host API serialises calls).
+__constant__ PipeParams cP;
+#define GL(p) __builtin_assume(__isGlobal(p))
+
 // Member functions copy the pointers they use into locals and tell the compiler that they point to
 // shared memory: otherwise every access is a generic LD/ST, and every store forces a reload of the
 // members of *this (which lives in local memory) because it might alias them.
@@ -141,7 +147,6 @@ template <bool GRAM>
 struct Warp {
   long long prof_cyc[PF_COUNT] = {0};
   Src cursrc;
-  const PipeParams &P;
   NnlsWs ws;
   GramWs gws;                    // Gram solver scratch
   double *V;                     // base of the Gram solver block in shared memory (gram.cuh layout)
@@ -162,7 +167,7 @@ struct Warp {
   unsigned long long n_early, n_overflow;
 
   __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
-      : P(p), sl(p.nTE, p.nT2, p.copy_elems, p.reg == 2) {
+      : sl(p.nTE, p.nT2, p.copy_elems, p.reg == 2) {
     SmemLayout L(p.nTE, p.nT2, p.rows_alloc, p.a_elems, p.gram);
     ws.A = smem + L.A, ws.b = smem + L.b, ws.u = smem + L.u, ws.x = smem + L.x, ws.w = smem + L.w;
     ws.idx = (int *)(smem + L.idx);
@@ -194,8 +199,8 @@ struct Warp {
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      mbar_expect_tx(bar, (unsigned)(P.copy_elems * 8));
-      tma_bulk_g2s(ws.A, src, (unsigned)(P.copy_elems * 8), bar);
+      mbar_expect_tx(bar, (unsigned)(cP.copy_elems * 8));
+      tma_bulk_g2s(ws.A, src, (unsigned)(cP.copy_elems * 8), bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -216,20 +221,20 @@ struct Warp {
   // ================= flip-angle fit =================
   // loss_with_grad!  src/splines.jl:1010-1041
   __device__ __noinline__ void fa_eval(int k, double &u, double &du) {
-    stage_matrix(P.basis_rm + (size_t)k * P.copy_elems);
+    stage_matrix(cP.basis_rm + (size_t)k * cP.copy_elems);
     nnls_warm_start<false>(ws, bd, 0.0, 0);
     NnlsOut o = nnls_core<false>(ws, 0.0);
     u = o.rnorm_sq;
-    const double *Ak = P.basis_cm + (size_t)k * P.nTE * P.nT2;
-    const double *dAk = P.dbasis_cm + (size_t)k * P.nTE * P.nT2;
+    const double *Ak = cP.basis_cm + (size_t)k * cP.nTE * cP.nT2;
+    const double *dAk = cP.dbasis_cm + (size_t)k * cP.nTE * cP.nT2;
     double acc = 0.0;
-    for (int i = lane; i < P.nTE; i += 32) {
+    for (int i = lane; i < cP.nTE; i += 32) {
       double ax = 0.0, dax = 0.0;
-      for (int j = 0; j < P.nT2; j++) {
+      for (int j = 0; j < cP.nT2; j++) {
         double xj = ws.x[j];
         if (xj > 0.0) {
-          ax = fma(xj, Ak[j * P.nTE + i], ax);
-          dax = fma(xj, dAk[j * P.nTE + i], dax);
+          ax = fma(xj, Ak[j * cP.nTE + i], ax);
+          dax = fma(xj, dAk[j * cP.nTE + i], dax);
         }
       }
       acc = fma(dax, ax - bd[i], acc);
@@ -279,7 +284,7 @@ struct Warp {
       double x_, u_;
       if (t < 0) {
         int I0 = __ffsll((long long)seen) - 1;
-        x_ = P.angles[I0], u_ = fu[I0];
+        x_ = cP.angles[I0], u_ = fu[I0];
       } else {
         // indices of the t-th and (t+1)-th set bits
         unsigned long long msk = seen;
@@ -287,7 +292,7 @@ struct Warp {
         int Ia = __ffsll((long long)msk) - 1;
         msk &= msk - 1;
         int Ib = __ffsll((long long)msk) - 1;
-        hermite_minimize(P.angles[Ia], P.angles[Ib], fu[Ia], fu[Ib], fdu[Ia], fdu[Ib], x_, u_);
+        hermite_minimize(cP.angles[Ia], cP.angles[Ib], fu[Ia], fu[Ib], fdu[Ia], fdu[Ib], x_, u_);
       }
       int ord = t + 1;
       // sequential semantics: the seed node always starts the scan; later candidates replace the
@@ -308,14 +313,14 @@ struct Warp {
   __device__ void basis_at(double alpha, long long v) {
     if constexpr (GRAM) {
       PROF_BEGIN(7);
-      if (P.epg_smem) epg_basis(alpha, v, V);  // lane <-> T2 component, states in the (idle) solver block
-      else if (P.nTE <= 63) epg_basis_shfl<false>(alpha, v);
+      if (cP.epg_smem) epg_basis(alpha, v, V);  // lane <-> T2 component, states in the (idle) solver block
+      else if (cP.nTE <= 63) epg_basis_shfl<false>(alpha, v);
       else epg_basis_shfl<true>(alpha, v);
       PROF_END(7);
       PROF_BEGIN(8);
       gram_build(g + sl.pristine);
       PROF_END(8);
-      cursrc.G = Gs, cursrc.ldg = P.ldg, cursrc.Arm = g + sl.pristine, cursrc.Acm = g + sl.pristine_cm;
+      cursrc.G = Gs, cursrc.ldg = cP.ldg, cursrc.Arm = g + sl.pristine, cursrc.Acm = g + sl.pristine_cm;
     } else {
       epg_basis(alpha, v, ws.A);
     }
@@ -336,8 +341,8 @@ struct Warp {
   __device__ __noinline__ double optimize_flip_angle() {
     unsigned long long seen = 0ull;
     int numeval = 0;
-    const int maxeval = P.maxeval, nA = P.nA;
-    for (int s = 0; s < P.nseed; s++) fa_probe(P.seeds[s], seen, numeval);
+    const int maxeval = cP.maxeval, nA = cP.nA;
+    for (int s = 0; s < cP.nseed; s++) fa_probe(cP.seeds[s], seen, numeval);
     double x, u;
     suggest_point(seen, x, u);
     while (true) {
@@ -345,7 +350,7 @@ struct Warp {
       int lo = 0, hi = nA - 1;
       while (true) {
         int mid = (lo + hi) / 2;
-        bool in_left = (P.angles[lo] <= x) && (x <= P.angles[mid]);
+        bool in_left = (cP.angles[lo] <= x) && (x <= cP.angles[mid]);
         int plo = in_left ? lo : mid, phi = in_left ? mid : hi;
         bool evaluated = ((seen >> plo) & 1ull) && ((seen >> phi) & 1ull);
         lo = plo, hi = phi;
@@ -353,7 +358,7 @@ struct Warp {
       }
       // evaluate_box! :802-815 with corners sorted by distance to x (stable)
       {
-        double d0 = __dmul_rn(P.angles[lo] - x, P.angles[lo] - x), d1 = __dmul_rn(P.angles[hi] - x, P.angles[hi] - x);
+        double d0 = __dmul_rn(cP.angles[lo] - x, cP.angles[lo] - x), d1 = __dmul_rn(cP.angles[hi] - x, cP.angles[hi] - x);
         int c0 = lo, c1 = hi;
         if (d1 < d0) c0 = hi, c1 = lo;
         int cs[2] = {c0, c1};
@@ -378,19 +383,21 @@ struct Warp {
   __device__ __noinline__ void epg_basis(double alpha_deg, long long v, double *S /* [3][K][32] shared scratch */) {
     const int lane = this->lane;
     SH(S);
-    const int ETL = P.nTE, n = P.nT2, ld = P.ld;
-    const int K = P.epg_kmax;
+    const int ETL = cP.nTE, n = cP.nT2, ld = cP.ld;
+    const int K = cP.epg_kmax;
     double *pr = g + sl.pristine;
-    double *pc = GRAM ? g + sl.pristine_cm : nullptr;
+    double *pc = GRAM ? g + sl.pristine_cm : pr;
+    GL(pr);
+    GL(pc);
     double sina, cosa;
     sincos(alpha_deg * 0.017453292519943295, &sina, &cosa);
     const double m0 = sind_0_180(alpha_deg / 2);
-    const double E1 = P.E1;
+    const double E1 = cP.E1;
 #define ST(c, k) S[((c)*K + (k)) * 32 + lane]
     for (int j0 = 0; j0 < n; j0 += 32) {
       const int j = j0 + lane;
       const bool act = j < n;
-      const double E2 = act ? P.E2[j] : 0.0;
+      const double E2 = act ? cP.E2[j] : 0.0;
       const double E2h = __dmul_rn(E2, E2) / 2, E1E2 = __dmul_rn(E1, E2), E1sq = __dmul_rn(E1, E1);
       const double a = E2h, b = __dmul_rn(E2h, cosa), c = __dmul_rn(E1E2, sina), d = __dmul_rn(E1sq, cosa);
       const double cp = -c / 2;
@@ -443,12 +450,12 @@ struct Warp {
     }
 #undef ST
 #undef UPD
-    dirty_rows = P.rows_alloc - P.nTE;  // the scratch overlapped the lambda rows
-    if (P.decaybasis && !P.fixed_alpha) {
+    dirty_rows = cP.rows_alloc - cP.nTE;  // the scratch overlapped the lambda rows
+    if (cP.decaybasis && !cP.fixed_alpha) {
       __syncwarp();
       for (int k = lane; k < ETL * n; k += 32) {
         int i = k % ETL, jj = k / ETL;
-        P.decaybasis[v + (long long)k * P.stride] = pr[i * ld + jj];
+        cP.decaybasis[v + (long long)k * cP.stride] = pr[i * ld + jj];
       }
     }
     __threadfence_block();
@@ -498,9 +505,9 @@ struct Warp {
     stage_matrix(Asrc);
     nnls_warm_start<true>(ws, bd, mu, dirty_rows);
     NnlsOut o = nnls_core<true>(ws, mu);
-    dirty_rows = o.rows_used - P.nTE;
-    double *sx = slots_x_p + cur_slot * P.nT2;
-    for (int j = lane; j < P.nT2; j += 32) sx[j] = ws.x[j];
+    dirty_rows = o.rows_used - cP.nTE;
+    double *sx = slots_x_p + cur_slot * cP.nT2;
+    for (int j = lane; j < cP.nT2; j += 32) sx[j] = ws.x[j];
     if (lane == 0) slot_mu[cur_slot] = mu, slot_r2[cur_slot] = o.rnorm_sq, slot_x2[cur_slot] = o.xnorm_sq;
     __syncwarp();
   }
@@ -833,7 +840,7 @@ struct Warp {
   // singular values of the voxel's basis by one-sided Jacobi on the smaller Gram-free side
   // (stands in for LAPACK dgesdd_, src/utils.jl:103-134).  lane <-> element of a column pair.
   __device__ __noinline__ void gcv_svdvals(const double *Asrc) {
-    const int m = P.nTE, n = P.nT2, ld = P.ld;
+    const int m = cP.nTE, n = cP.nT2, ld = cP.ld;
     double *Gm = g + sl.gcv_mat;  // tall r x c, column-major
     const int r = m >= n ? m : n, c = m >= n ? n : m;
     for (int k = lane; k < m * n; k += 32) {
@@ -877,7 +884,7 @@ struct Warp {
     __syncwarp();
   }
   __device__ __noinline__ double gcv_fun(double logmu, const double *Asrc) {  // log(max(gcv, eps^2/m))  :1150-1154, 1213-1229
-    const int m = P.nTE, n = P.nT2;
+    const int m = cP.nTE, n = cP.nT2;
     double mu = exp(logmu);
     cache_solve(mu, Asrc);
     double r2 = cur_resnorm_sq();
@@ -946,11 +953,12 @@ struct Warp {
   // =====================================================================================
   // c = A' bd  (lane <-> column, coalesced rows of the row-major matrix)
   __device__ __noinline__ void gram_rhs(const double *Arm) {
+    GL(Arm);
     const int lane = this->lane;
     VIEW(double, bd);
     VIEW(double, cvec);
-    const int nTE = P.nTE, ld = P.ld;
-    _Pragma("unroll 1") for (int j = lane; j < P.nT2; j += 32) {
+    const int nTE = cP.nTE, ld = cP.ld;
+    _Pragma("unroll 1") for (int j = lane; j < cP.nT2; j += 32) {
       const double *col = Arm + j;
       double a = 0.0;
       _Pragma("unroll 8") for (int i = 0; i < nTE; i++) a = fma(col[i * ld], bd[i], a);  // the matrix lives in L2: 8 loads in flight
@@ -961,11 +969,12 @@ struct Warp {
 
   // explicit residual r = bd - A_P s (stored in `fit`), returns ||r||^2.  lane <-> echo.
   __device__ __noinline__ double gram_residual(const double *Acm, int k) {
+    GL(Acm);
     const int lane = this->lane;
     VIEW(double, bd);
     VIEW(double, fit);
     VIEW_GWS();
-    const int nTE = P.nTE;
+    const int nTE = cP.nTE;
     double acc = 0.0;
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
       double r = bd[i];
@@ -981,13 +990,14 @@ struct Warp {
   // one step of iterative refinement on the active set: s += (G_PP + mu2 I)^-1 (A_P' r - mu2 s),
   // with r = bd - A_P s already in `fit`.  Restores QR-level accuracy of the normal-equation solve.
   __device__ __noinline__ void gram_refine(const double *Acm, int k, double mu2) {
+    GL(Acm);
     const int lane = this->lane;
     VIEW(double, fit);
     VIEW(double, Gs);
     VIEW_GWS();
-    const int nTE = P.nTE;
+    const int nTE = cP.nTE;
     double *T = Gs;
-    const int ld = P.ldg;
+    const int ld = cP.ldg;
     // g_t = A[:,P[t]]' r - mu2 s_t: lane <-> echo (coalesced L2 reads, all lanes busy), two columns per round
     _Pragma("unroll 1") for (int t = 0; t < k; t += 2) {
       const int t1c = t + 1 < k ? t + 1 : t;
@@ -1027,20 +1037,20 @@ struct Warp {
   }
 
   // unregularised NNLS following the reference's cold-start path, polished by one refinement step;
-  // returns ||A x - b||^2 (explicit) and leaves r in `fit`, x in gws.x, the active set in gws.P.
+  // returns ||A x - b||^2 (explicit) and leaves r in `fit`, x in gws.x, the active set in gws.cP.
   // `warm_mask` != 0: start from that active set instead (flip-angle probes only: the loss and its
   // gradient depend on the minimiser, which is unique, not on the pivoting path).
   __device__ __noinline__ double gram_solve_unreg(const Src &src, GramOut &o, unsigned long long warm_mask = 0ull) {
     const int lane = this->lane;
     VIEW(double, V);
     VIEW_GWS();
-    const int max_set = P.nTE < P.nT2 ? P.nTE : P.nT2;
+    const int max_set = cP.nTE < cP.nT2 ? cP.nTE : cP.nT2;
     if (warm_mask) {
-      _Pragma("unroll 1") for (int j = lane; j < P.nT2; j += 32) gws.x[j] = ((warm_mask >> j) & 1ull) ? 1.0 : 0.0;
+      _Pragma("unroll 1") for (int j = lane; j < cP.nT2; j += 32) gws.x[j] = ((warm_mask >> j) & 1ull) ? 1.0 : 0.0;
       __syncwarp();
     }
     PROF_BEGIN(1);
-    o = gram_nnls(V, P.nT2, P.ldg, 0.0, max_set, warm_mask != 0ull, warm_mask);
+    o = gram_nnls(V, cP.nT2, cP.ldg, 0.0, max_set, warm_mask != 0ull, warm_mask);
     PROF_END(1);
     PROF_BEGIN(2);
     double r2 = gram_residual(src.Acm, o.k);
@@ -1063,20 +1073,20 @@ struct Warp {
     VIEW(double, Gs);
     VIEW(unsigned long long, fa_mask_p);
     VIEW_GWS();
-    const int nTE = P.nTE, n = P.nT2;
+    const int nTE = cP.nTE, n = cP.nT2;
     Src src;
-    src.G = P.gram_set + (size_t)kang * P.a_elems, src.ldg = P.ldg;
-    src.Arm = P.basis_rm + (size_t)kang * P.copy_elems;
-    src.Acm = P.basis_cm + (size_t)kang * nTE * n;
+    src.G = cP.gram_set + (size_t)kang * cP.a_elems, src.ldg = cP.ldg;
+    src.Arm = cP.basis_rm + (size_t)kang * cP.copy_elems;
+    src.Acm = cP.basis_cm + (size_t)kang * nTE * n;
     PROF_BEGIN(5);
-    stage_bulk(Gs, src.G, (unsigned)(P.a_elems * 8));  // TMA: G_k (lower triangle valid) -> shared memory
+    stage_bulk(Gs, src.G, (unsigned)(cP.a_elems * 8));  // TMA: G_k (lower triangle valid) -> shared memory
     PROF_END(5);
     PROF_BEGIN(0);
     gram_rhs(src.Arm);
     PROF_END(0);
     // warm start from the active set found at the nearest angle already probed
     unsigned long long warm = 0ull;
-    if (seen && P.fa_warm) {
+    if (seen && cP.fa_warm) {
       unsigned long long below = seen & ((1ull << kang) - 1ull), above = seen >> kang;  // bit kang itself is never set
       int jb = below ? 63 - __clzll((long long)below) : -1000;
       int ja = above ? kang + __ffsll((long long)above) - 1 : 1000;
@@ -1086,7 +1096,8 @@ struct Warp {
     GramOut o;
     u = gram_solve_unreg(src, o, warm);
     if (lane == 0) fa_mask_p[kang] = o.mask;
-    const double *dAk = P.dbasis_cm + (size_t)kang * nTE * n;
+    const double *dAk = cP.dbasis_cm + (size_t)kang * nTE * n;
+    GL(dAk);
     double acc = 0.0;
     PROF_BEGIN(4);
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
@@ -1108,12 +1119,12 @@ struct Warp {
   // resp. <= 127 with the second register set).
   template <bool TWO>
   __device__ __noinline__ void epg_basis_shfl(double alpha_deg, long long v) {
-    const int ETL = P.nTE, n = P.nT2, ld = P.ld;
+    const int ETL = cP.nTE, n = cP.nT2, ld = cP.ld;
     double *prm = g + sl.pristine, *pcm = g + sl.pristine_cm;
     double sina, cosa;
     sincos(alpha_deg * 0.017453292519943295, &sina, &cosa);
     const double m0 = sind_0_180(alpha_deg / 2);
-    const double E1 = P.E1;
+    const double E1 = cP.E1;
     constexpr int NS = TWO ? 2 : 1;
     for (int j0 = 0; j0 < n; j0 += 4) {
       double a[4], b[4], c[4], d[4], cp[4];
@@ -1121,7 +1132,7 @@ struct Warp {
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int j = (j0 + q < n) ? j0 + q : n - 1;
-        const double E2 = P.E2[j];
+        const double E2 = cP.E2[j];
         const double E2h = __dmul_rn(E2, E2) / 2, E1E2 = __dmul_rn(E1, E2), E1sq = __dmul_rn(E1, E1);
         a[q] = E2h, b[q] = __dmul_rn(E2h, cosa), c[q] = __dmul_rn(E1E2, sina), d[q] = __dmul_rn(E1sq, cosa);
         cp[q] = -c[q] / 2;
@@ -1177,17 +1188,18 @@ struct Warp {
       }
     }
     __syncwarp();
-    if (P.decaybasis && !P.fixed_alpha) {
-      _Pragma("unroll 1") for (int k = lane; k < ETL * n; k += 32) P.decaybasis[v + (long long)k * P.stride] = pcm[k];
+    if (cP.decaybasis && !cP.fixed_alpha) {
+      _Pragma("unroll 1") for (int k = lane; k < ETL * n; k += 32) cP.decaybasis[v + (long long)k * cP.stride] = pcm[k];
     }
   }
 
   // G = A'A and c = A'bd from the row-major basis in global scratch into shared memory.
   // lane <-> column q, four rows p of G at a time.
   __device__ __noinline__ void gram_build(const double *Arm) {
+    GL(Arm);
     const int lane = this->lane;
     VIEW(double, Gs);
-    const int nTE = P.nTE, n = P.nT2, ld = P.ld, ldg = P.ldg;
+    const int nTE = cP.nTE, n = cP.nT2, ld = cP.ld, ldg = cP.ldg;
     for (int p0 = 0; p0 < n; p0 += 4) {
       const int qmax = (p0 + 3 < n) ? p0 + 3 : n - 1;  // only q <= p is stored
       for (int qb = 0; qb <= qmax; qb += 32) {
@@ -1219,7 +1231,7 @@ struct Warp {
     VIEW(double, slots_x_p);
     VIEW(double, V);
     VIEW_GWS();
-    const int n = P.nT2;
+    const int n = cP.nT2;
     int hit = -1, firstnan = -1, nearest = -1;
     double dbest = CUDART_INF;
     _Pragma("unroll 1") for (int i = 0; i < DECAES_NCACHE; i++) {
@@ -1247,12 +1259,12 @@ struct Warp {
       __syncwarp();
     }
     PROF_BEGIN(9);
-    o = gram_nnls(V, n, P.ldg, mu2, n, nearest >= 0, nearest >= 0 ? slot_mask[nearest] : 0ull);
+    o = gram_nnls(V, n, cP.ldg, mu2, n, nearest >= 0, nearest >= 0 ? slot_mask[nearest] : 0ull);
     PROF_END(9);
     PROF_BEGIN(2);
     double r2 = gram_residual(src.Acm, o.k);
     PROF_END(2);
-    if (o.k > 0 && P.refine_tikh) {
+    if (o.k > 0 && cP.refine_tikh) {
       // one refinement step on the explicit residual: x(mu) accurate to ~cond([A; mu I]) * eps, so
       // that ||Ax - b||^2 and ||x||^2 (the inputs of the mu searches) carry reference-level noise
       gram_refine(src.Acm, o.k, mu2);
@@ -1276,14 +1288,14 @@ struct Warp {
   double max_signal_cur, alpha_cur;
 
   // phase 1: normalise (src/T2mapSEcorr.jl:205-218) and fit the flip angle (:409-423)
-  __device__ __noinline__ void phase_flip_angle(long long v, const double *signal /* global: image + v, echo stride P.stride */) {
+  __device__ __noinline__ void phase_flip_angle(long long v, const double *signal /* global: image + v, echo stride cP.stride */) {
     const int lane = this->lane;
     VIEW(double, bd);
-    const int nTE = P.nTE;
+    const int nTE = cP.nTE;
     v_cur = v;
     double mx = 0.0;
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
-      double bi = __ldg(signal + (long long)i * P.stride);
+      double bi = __ldg(signal + (long long)i * cP.stride);
       bd[i] = bi;
       mx = bi > mx ? bi : mx;
     }
@@ -1292,17 +1304,17 @@ struct Warp {
     if (max_signal > 0)
       _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) bd[i] = ddiv(bd[i], max_signal);
     __syncwarp();
-    if (P.alpha_provided) alpha_cur = P.alpha[v];
-    else if (P.fixed_alpha) alpha_cur = P.SetFlipAngle;
+    if (cP.alpha_provided) alpha_cur = cP.alpha[v];
+    else if (cP.fixed_alpha) alpha_cur = cP.SetFlipAngle;
     else alpha_cur = optimize_flip_angle();
   }
 
   // phase 2: EPG basis at the fitted angle (+ Gram matrix / right-hand side)
   __device__ __noinline__ void phase_basis() {
-    if (P.fixed_alpha && !P.alpha_provided) {
+    if (cP.fixed_alpha && !cP.alpha_provided) {
       if constexpr (GRAM) {
-        cursrc.G = P.gram_set, cursrc.ldg = P.ldg, cursrc.Arm = P.basis_rm, cursrc.Acm = P.basis_cm;
-        stage_bulk(Gs, P.gram_set, (unsigned)(P.a_elems * 8));
+        cursrc.G = cP.gram_set, cursrc.ldg = cP.ldg, cursrc.Arm = cP.basis_rm, cursrc.Acm = cP.basis_cm;
+        stage_bulk(Gs, cP.gram_set, (unsigned)(cP.a_elems * 8));
         gram_rhs(cursrc.Arm);
       }
     } else {
@@ -1320,16 +1332,16 @@ struct Warp {
     const NnlsWs ws = this->ws;
     SH(ws.x);
     SH(ws.w);
-    const int nTE = P.nTE, n = P.nT2;
+    const int nTE = cP.nTE, n = cP.nT2;
     const long long v = v_cur;
     const double max_signal = max_signal_cur, alpha = alpha_cur;
-    const double *Asrc = (P.fixed_alpha && !P.alpha_provided) ? P.basis_rm : g + sl.pristine;
+    const double *Asrc = (cP.fixed_alpha && !cP.alpha_provided) ? cP.basis_rm : g + sl.pristine;
 
     // T2_distribution!  src/T2mapSEcorr.jl:475-505
     double mu = CUDART_NAN, chi2 = CUDART_NAN;
     int src_kind = 0;  // 0: ws.x (unregularised solve just done), 1: cache slot, 2: zeros
-    const bool want_chi2 = (P.chi2factor != nullptr);
-    switch (P.reg) {
+    const bool want_chi2 = (cP.chi2factor != nullptr);
+    switch (cP.reg) {
       case 0: {
         mu = 0.0, chi2 = 1.0;
         solve_unreg(Asrc);
@@ -1366,12 +1378,12 @@ struct Warp {
         bool early = false;
         double target, ftol;
         int mode;
-        if (P.reg == 3) {
+        if (cP.reg == 3) {
           early = (res2_min == 0 || o.nsetp == 0);
-          target = __dmul_rn(P.Chi2Factor, res2_min), ftol = 1e-3 * (P.Chi2Factor - 1), mode = 0;
+          target = __dmul_rn(cP.Chi2Factor, res2_min), ftol = 1e-3 * (cP.Chi2Factor - 1), mode = 0;
           if (early) mu = 0.0, chi2 = 1.0;
         } else {
-          double sigma = P.NoiseLevel / max_signal;
+          double sigma = cP.NoiseLevel / max_signal;
           double delta = __dmul_rn(sqrt((double)nTE), sigma);
           double acc = 0.0;
           for (int i = lane; i < nTE; i += 32) acc = fma(bd[i], bd[i], acc);
@@ -1435,7 +1447,7 @@ struct Warp {
     } else {
       stage_matrix(Asrc);  // pristine basis back into shared memory for fit = A x
       for (int i = lane; i < nTE; i += 32) {
-        const double *row = ws.A + i * P.ld;
+        const double *row = ws.A + i * cP.ld;
         double s0 = 0.0;
         for (int j = 0; j < n; j++) s0 = fma(row[j], xs[j], s0);
         fit[i] = s0;
@@ -1455,40 +1467,40 @@ struct Warp {
     }
     var = warp_sum(var);
     double S = 0.0, dotl = 0.0;
-    for (int j = lane; j < n; j += 32) S += xs[j], dotl = fma(xs[j], P.logT2[j], dotl);
+    for (int j = lane; j < n; j += 32) S += xs[j], dotl = fma(xs[j], cP.logT2[j], dotl);
     S = warp_sum(S), dotl = warp_sum(dotl);
     double log_ggm = dotl / S;
     double l1p = 0.0;
     for (int j = lane; j < n; j += 32) {
-      double dlt = P.logT2[j] - log_ggm;
+      double dlt = cP.logT2[j] - log_ggm;
       l1p = fma(__dmul_rn(dlt, dlt), xs[j], l1p);
     }
     l1p = warp_sum(l1p) / S;
 
     if (lane == 0) {
-      P.gdn[v] = S;
-      P.ggm[v] = exp(log_ggm);
-      P.gva[v] = expm1(l1p);
-      P.fnr[v] = S / sqrt(r2 / (nTE - 1));
-      P.snr[v] = max_signal / sqrt(var / (nTE - 1));
-      P.alpha[v] = alpha;
-      if (P.mu && P.chi2factor) P.mu[v] = mu, P.chi2factor[v] = chi2;
-      if (P.resnorm) P.resnorm[v] = sqrt(r2);
+      cP.gdn[v] = S;
+      cP.ggm[v] = exp(log_ggm);
+      cP.gva[v] = expm1(l1p);
+      cP.fnr[v] = S / sqrt(r2 / (nTE - 1));
+      cP.snr[v] = max_signal / sqrt(var / (nTE - 1));
+      cP.alpha[v] = alpha;
+      if (cP.mu && cP.chi2factor) cP.mu[v] = mu, cP.chi2factor[v] = chi2;
+      if (cP.resnorm) cP.resnorm[v] = sqrt(r2);
     }
-    for (int j = lane; j < n; j += 32) P.dist[v + (long long)j * P.stride] = xs[j];
-    if (P.decaycurve)
-      for (int i = lane; i < nTE; i += 32) P.decaycurve[v + (long long)i * P.stride] = fit[i];
+    for (int j = lane; j < n; j += 32) cP.dist[v + (long long)j * cP.stride] = xs[j];
+    if (cP.decaycurve)
+      for (int i = lane; i < nTE; i += 32) cP.decaycurve[v + (long long)i * cP.stride] = fit[i];
 
     // fused T2part epilogue  src/T2partSEcorr.jl:95-138
-    if (P.has_part) {
+    if (cP.has_part) {
       bool isn = false;
       double Ssp = 0, Smp = 0, dsp = 0, dmp = 0, dw = 0;
       for (int j = lane; j < n; j += 32) {
         double dj = xs[j];
         isn |= isnan(dj);
-        if (j >= P.sp_lo && j <= P.sp_hi) dsp += __dmul_rn(dj, P.logT2[j]), Ssp += dj;
-        if (j >= P.mp_lo && j <= P.mp_hi) dmp += __dmul_rn(dj, P.logT2[j]), Smp += dj;
-        if (P.has_sigmoid) dw = fma(dj, P.weights[j], dw);
+        if (j >= cP.sp_lo && j <= cP.sp_hi) dsp += __dmul_rn(dj, cP.logT2[j]), Ssp += dj;
+        if (j >= cP.mp_lo && j <= cP.mp_hi) dmp += __dmul_rn(dj, cP.logT2[j]), Smp += dj;
+        if (cP.has_sigmoid) dw = fma(dj, cP.weights[j], dw);
       }
       Ssp = warp_sum(Ssp), Smp = warp_sum(Smp), dsp = warp_sum(dsp), dmp = warp_sum(dmp), dw = warp_sum(dw);
       const bool anynan = __any_sync(DECAES_FULL_MASK, isn);
@@ -1496,11 +1508,11 @@ struct Warp {
         // entries the reference leaves untouched keep its NaN pre-fill (src/T2partSEcorr.jl:83-90)
         double sfr = CUDART_NAN, mfr = CUDART_NAN, sgm = CUDART_NAN, mgm = CUDART_NAN;
         if (!anynan) {
-          if (S > 0) sfr = P.has_sigmoid ? dw / S : Ssp / S, mfr = Smp / S;
+          if (S > 0) sfr = cP.has_sigmoid ? dw / S : Ssp / S, mfr = Smp / S;
           if (Ssp > 0) sgm = exp(dsp / Ssp);
           if (Smp > 0) mgm = exp(dmp / Smp);
         }
-        P.sfr[v] = sfr, P.mfr[v] = mfr, P.sgm[v] = sgm, P.mgm[v] = mgm;
+        cP.sfr[v] = sfr, cP.mfr[v] = mfr, cP.sgm[v] = sgm, cP.mgm[v] = mgm;
       }
     }
     __syncwarp();
