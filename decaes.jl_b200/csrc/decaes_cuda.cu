@@ -153,6 +153,21 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
   fence_proxy_async();
   __syncwarp();
 
+  // Phase barriers: CTA-wide (sync_groups = 1) or per group of warps that share an SM sub-partition
+  // (warp id mod 4; sync_groups = 4), so that fewer warps wait for the slowest one of their group.
+  const int nwarps = blockDim.x >> 5;
+  const int grp = (P.sync_groups > 1) ? (wid % P.sync_groups) : 0;
+  const int gthreads = 32 * ((nwarps - grp + (P.sync_groups > 1 ? P.sync_groups : 1) - 1) / (P.sync_groups > 1 ? P.sync_groups : 1));
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(gthreads) : "memory"); };
+  auto group_or = [&](bool pred) -> bool {
+    int r;
+    asm volatile(
+        "{\n.reg .pred p, q;\nsetp.ne.b32 p, %3, 0;\nbarrier.red.or.pred q, %1, %2, p;\nselp.b32 %0, 1, 0, q;\n}\n"
+        : "=r"(r)
+        : "r"(grp + 1), "r"(gthreads), "r"((int)pred)
+        : "memory");
+    return r != 0;
+  };
   const long long ngroups = (P.nvox + DECAES_GROUP - 1) / DECAES_GROUP;
   unsigned long long processed = 0;
   long long cyc[4] = {0, 0, 0, 0};  // per-warp cycles: barrier wait, flip angle, basis, solve+save
@@ -205,15 +220,15 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
       }
     }
     long long t0 = clock64();
-    if (!__syncthreads_or(have)) break;  // every warp of the CTA is out of work
+    if (!group_or(have)) break;  // every warp of the group is out of work
     long long t1 = clock64();
     if (have) W.phase_flip_angle(v, signal);
     long long t2 = clock64();
-    if (P.sync_mask & 1) __syncthreads();
+    if (P.sync_mask & 1) group_sync();
     long long t3 = clock64();
     if (have) W.phase_basis();
     long long t4 = clock64();
-    if (P.sync_mask & 2) __syncthreads();
+    if (P.sync_mask & 2) group_sync();
     long long t5 = clock64();
     if (have) {
       W.phase_solve_and_save();
@@ -520,6 +535,8 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.refine_tikh = (o->reg != DECAES_REG_LCURVE);
   if (const char *e = getenv("DECAES_REFINE")) P.refine_tikh = atoi(e);
   P.sync_mask = 3;
+  P.sync_groups = 1;
+  if (const char *e = getenv("DECAES_SYNC_GROUPS")) P.sync_groups = std::max(1, atoi(e));
   P.fa_warm = 1;
   if (const char *e = getenv("DECAES_FA_WARM")) P.fa_warm = atoi(e);
   if (const char *e = getenv("DECAES_SYNC_MASK")) P.sync_mask = atoi(e);

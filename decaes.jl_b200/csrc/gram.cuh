@@ -243,6 +243,54 @@ __device__ __noinline__ int gram_refactor(double *V, int ld, int k, double mu2) 
   return kk;
 }
 
+// Remove pivot position r from the factorisation (k <= 32 columns) by Givens rotations instead of a
+// refactorisation: rotating rows (i, i+1), i = r..k-2, of M pushes the mass of column r into the last
+// row; dropping that row and column r leaves the inverse Cholesky factor of the reduced block (up to
+// row signs, which neither the append formulas nor s = M'y care about).  lane <-> column u of M: a
+// rotation touches only the lane's own two entries, the rotation coefficients follow from column r
+// alone and are computed redundantly by every lane; lane r (whose column disappears) carries y.
+// The caller compacts P and recomputes s (gram_solve_s) once all removals are done.
+__device__ __noinline__ void gram_downdate(double *V, int ld, int k, int r) {
+  __builtin_assume(__isShared(V));
+  const int lane = lane_id();
+  double *T = V + GV_T;
+  const int u = lane;                      // this lane's column
+  const int ud = u - (u > r ? 1 : 0);      // ... and where it ends up
+  const bool isy = (u == r);
+  double a = GM_(r, r);                    // running (i, r) entry
+  double carry = isy ? V[GV_Y + r] : (u < r ? GM_(r, u) : 0.0);
+  _Pragma("unroll 1") for (int i = r; i < k - 1; i++) {
+    const double b = GM_(i + 1, r);
+    const double h2 = fma(a, a, b * b);
+    const double hinv = rsqrt(h2);
+    const double c = b * hinv, sn = a * hinv;
+    a = h2 * hinv;
+    double e = 0.0;
+    if (isy) e = V[GV_Y + i + 1];
+    else if (u < k && u <= i + 1) e = GM_(i + 1, u);
+    const double ni = c * carry - sn * e;
+    carry = fma(sn, carry, c * e);
+    // one barrier per rotation: row i was last read in the previous iteration (and M(r,r) before the
+    // loop); it is overwritten now (a lane writes into its left neighbour's column)
+    __syncwarp();
+    if (isy) V[GV_Y + i] = ni;
+    else if (u < k && u <= i + 1) GM_(i, ud) = ni;
+  }
+  __syncwarp();
+}
+
+// s = M'y for the current factorisation
+__device__ __forceinline__ void gram_solve_s(double *V, int ld, int k) {
+  const int lane = lane_id();
+  double *T = V + GV_T;
+  _Pragma("unroll 1") for (int u = lane; u < k; u += 32) {
+    double a = 0.0;
+    _Pragma("unroll 4") for (int t = u; t < k; t++) a = fma(GM_(t, u), V[GV_Y + t], a);
+    V[GV_S + u] = a;
+  }
+  __syncwarp();
+}
+
 // Lawson–Hanson main loop.  cold: start from the empty set with the reference's warm dual
 // (src/lsqnonneg.jl:44-70).  warm: start from the feasible point x supported on `mask`.
 __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, int max_set, bool warm, unsigned long long mask) {
@@ -339,10 +387,18 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
       }
       __syncwarp();
       // remove imv, then any other non-positive coefficient (first found), compacting P
+      const bool small = k <= 32;
       while (true) {
-        if (lane == 0) {
-          V[GV_X + P[imv]] = 0.0;
-          for (int t = imv; t < k - 1; t++) P[t] = P[t + 1];
+        if (small) gram_downdate(V, ld, k, imv);
+        int pn = 0;
+        if (lane >= imv && lane < k - 1) pn = P[lane + 1];
+        if (lane == 0) V[GV_X + P[imv]] = 0.0;
+        __syncwarp();
+        if (k > 32) {
+          if (lane == 0)
+            for (int t = imv; t < k - 1; t++) P[t] = P[t + 1];
+        } else if (lane >= imv && lane < k - 1) {
+          P[lane] = pn;
         }
         __syncwarp();
         k -= 1;
@@ -352,6 +408,11 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
         bad = __reduce_min_sync(DECAES_FULL_MASK, bad);
         if (bad == 0x7fffffffu) break;
         imv = (int)bad;
+      }
+      if (small) {
+        gram_solve_s(V, ld, k);
+        mask = mask_of(P, k);
+        continue;
       }
       k = gram_refactor(V, ld, k, mu2);
       mask = mask_of(P, k);

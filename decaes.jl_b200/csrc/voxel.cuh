@@ -38,6 +38,7 @@ struct PipeParams {
   int gram, ldg;            // solver variant (1 = normal-equation active set), leading dimension of G
   int warps_per_cta, smem_per_warp;  // CTA shape: bytes of dynamic shared memory owned by each warp
   int fa_warm;              // warm-start flip-angle probes from the nearest probed angle (Gram solver)
+  int sync_groups;          // 1: CTA-wide phase barriers; g > 1: one barrier per group of warps (warp id mod g)
   int sync_mask;            // which intra-round CTA barriers are active (bit 0: after flip angle, bit 1: after basis)
   int epg_smem;             // EPG at the fitted angle keeps its states in shared memory (lane <-> component)
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
@@ -975,13 +976,19 @@ struct Warp {
     VIEW(double, fit);
     VIEW_GWS();
     const int nTE = cP.nTE;
-    double acc = 0.0;
-    _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
-      double r = bd[i];
-      _Pragma("unroll 4") for (int t = 0; t < k; t++) r = fma(-Acm[gws.P[t] * nTE + i], gws.s[t], r);
-      fit[i] = r;
-      acc = fma(r, r, acc);
+    // lane <-> echoes lane, lane + 32 (, lane + 64): all of them advance together so that one L2 round
+    // trip serves up to 12 loads per lane (A lives in L2; the loop is latency bound)
+    const int i0 = lane, i1 = lane + 32 < nTE ? lane + 32 : lane, i2 = lane + 64 < nTE ? lane + 64 : lane;
+    double r0 = bd[i0], r1 = bd[i1], r2 = bd[i2];
+    _Pragma("unroll 4") for (int t = 0; t < k; t++) {
+      const double *col = Acm + gws.P[t] * nTE;
+      const double st = gws.s[t];
+      r0 = fma(-col[i0], st, r0), r1 = fma(-col[i1], st, r1), r2 = fma(-col[i2], st, r2);
     }
+    double acc = 0.0;
+    if (lane < nTE) fit[i0] = r0, acc = __dmul_rn(r0, r0);
+    if (lane + 32 < nTE) fit[i1] = r1, acc = fma(r1, r1, acc);
+    if (lane + 64 < nTE) fit[i2] = r2, acc = fma(r2, r2, acc);
     acc = warp_sum(acc);
     __syncwarp();
     return acc;
