@@ -958,13 +958,16 @@ struct Warp {
     const int lane = this->lane;
     VIEW(double, bd);
     VIEW(double, cvec);
-    const int nTE = cP.nTE, ld = cP.ld;
-    _Pragma("unroll 1") for (int j = lane; j < cP.nT2; j += 32) {
-      const double *col = Arm + j;
-      double a = 0.0;
-      _Pragma("unroll 8") for (int i = 0; i < nTE; i++) a = fma(col[i * ld], bd[i], a);  // the matrix lives in L2: 8 loads in flight
-      cvec[j] = a;
+    const int nTE = cP.nTE, ld = cP.ld, n = cP.nT2;
+    // lane <-> columns lane and lane + 32: both advance together, 16 loads in flight (the matrix lives in L2)
+    const double *c0 = Arm + (lane < n ? lane : 0), *c1 = Arm + (lane + 32 < n ? lane + 32 : 0);
+    double a0 = 0.0, a1 = 0.0;
+    _Pragma("unroll 8") for (int i = 0; i < nTE; i++) {
+      const double bi = bd[i];
+      a0 = fma(c0[i * ld], bi, a0), a1 = fma(c1[i * ld], bi, a1);
     }
+    if (lane < n) cvec[lane] = a0;
+    if (lane + 32 < n) cvec[lane + 32] = a1;
     __syncwarp();
   }
 
@@ -1200,29 +1203,45 @@ struct Warp {
     }
   }
 
-  // G = A'A and c = A'bd from the row-major basis in global scratch into shared memory.
-  // lane <-> column q, four rows p of G at a time.
+  // G = A'A (lower triangle) and c = A'bd from the row-major basis in global scratch into shared memory.
+  // The Gram contraction runs on the FP64 tensor cores: mma.sync m8n8k4 with D(p, q) += sum over four
+  // echoes of A(i, p) A(i, q); both operand fragments are the SAME load pattern (lane (g, t) holds
+  // A[i0 + t][8 c + g]), one 8-column tile row of G at a time.
   __device__ __noinline__ void gram_build(const double *Arm) {
     GL(Arm);
     const int lane = this->lane;
     VIEW(double, Gs);
     const int nTE = cP.nTE, n = cP.nT2, ld = cP.ld, ldg = cP.ldg;
-    for (int p0 = 0; p0 < n; p0 += 4) {
-      const int qmax = (p0 + 3 < n) ? p0 + 3 : n - 1;  // only q <= p is stored
-      for (int qb = 0; qb <= qmax; qb += 32) {
-        const int q = qb + lane;
-        const bool act = q <= qmax;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int i = 0; i < nTE; i++) {
-          const double *row = Arm + i * ld;
-          const double aq = act ? row[q] : 0.0;
+    const int g = lane >> 2, t = lane & 3;
+    const int NT = (n + 7) >> 3;
+    _Pragma("unroll 1") for (int cp = 0; cp < NT; cp++) {
+      double acc[8][2];
 #pragma unroll
-          for (int r = 0; r < 4; r++) acc[r] = fma(row[(p0 + r < n) ? p0 + r : n - 1], aq, acc[r]);
-        }
+      for (int cq = 0; cq < 8; cq++) acc[cq][0] = acc[cq][1] = 0.0;
+      const bool pv = 8 * cp + g < n;
+      _Pragma("unroll 1") for (int i0 = 0; i0 < nTE; i0 += 4) {
+        const bool iv = i0 + t < nTE;
+        const double *row = Arm + (iv ? i0 + t : 0) * ld + g;
+        const double fa = (iv && pv) ? row[8 * cp] : 0.0;
+        double f[8];
 #pragma unroll
-        for (int r = 0; r < 4; r++)
-          if (act && p0 + r < n && q <= p0 + r) Gs[(p0 + r) * ldg + q] = acc[r];
+        for (int cq = 0; cq < 8; cq++)
+          if (cq <= cp) f[cq] = (iv && 8 * cq + g < n) ? row[8 * cq] : 0.0;
+#pragma unroll
+        for (int cq = 0; cq < 8; cq++)
+          if (cq <= cp)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(acc[cq][0]), "+d"(acc[cq][1])
+                         : "d"(fa), "d"(f[cq]));
       }
+      const int p = 8 * cp + g;
+#pragma unroll
+      for (int cq = 0; cq < 8; cq++)
+        if (cq <= cp && p < n) {
+          const int q = 8 * cq + 2 * t;
+          if (q <= p) Gs[p * ldg + q] = acc[cq][0];
+          if (q + 1 <= p) Gs[p * ldg + q + 1] = acc[cq][1];
+        }
     }
     __syncwarp();
     gram_rhs(Arm);
