@@ -92,9 +92,67 @@ __device__ static void epg_curve_jac(int ETL, double alpha_deg, double E1, doubl
 #undef LOADK
 }
 
+// General refocusing-control-angle variant (RefConAngle != 180): first refocusing pulse A*180 = alpha,
+// later pulses A*beta with A = alpha/180 (src/EPGdecaycurve.jl:722-818).  Same in-place state update as
+// above with the three dot products F.M, Fbar.M, Z.M per state; value + d/dalpha (per degree).
+__device__ static void epg_curve_beta_jac(int ETL, double alpha_deg, double beta_deg, double E1, double E2, double *dc,
+                                          double *ddc, int out_stride) {
+  const double kk = 0.017453292519943295;
+  const double A = alpha_deg / 180;
+  const double a1r = (A * 180) * kk, air = (A * beta_deg) * kk;
+  const double kb = (beta_deg / 180) * kk;  // d(air)/d(alpha_deg)
+  double sh, ch, sini, cosi;
+  sincos(a1r / 2, &sh, &ch);
+  sincos(air, &sini, &cosi);
+  const double dsh = ch * (kk / 2), dch = -sh * (kk / 2);
+  const double s2h = sh * sh, c2h = ch * ch, ds2h = 2 * sh * dsh, dc2h = 2 * ch * dch;
+  const double sin1 = 2 * sh * ch, dsin1 = 2 * (dsh * ch + sh * dch);
+  const double dsini = cosi * kb, dcosi = -sini * kb;
+  const double c2hi = (1 + cosi) / 2, s2hi = 1 - c2hi, dc2hi = dcosi / 2, ds2hi = -dc2hi;
+  const double E2sq = E2 * E2, E1E2 = E1 * E2, E1sq = E1 * E1;
+  const double a1 = E2sq * c2h, b1 = E2sq * s2h, c1 = E1E2 * sin1;
+  const double da1 = E2sq * dc2h, db1 = E2sq * ds2h, dc1 = E1E2 * dsin1;
+  const double ai = E2sq * c2hi, bi = E2sq * s2hi, ci = E1E2 * sini, di = E1sq * cosi;
+  const double dai = E2sq * dc2hi, dbi = E2sq * ds2hi, dci = E1E2 * dsini, ddi = E1sq * dcosi;
+  const double Fv[3] = {ai, bi, ci}, Fbv[3] = {bi, ai, -ci}, Zv[3] = {-ci / 2, ci / 2, di};
+  const double dFv[3] = {dai, dbi, dci}, dFbv[3] = {dbi, dai, -dci}, dZv[3] = {-dci / 2, dci / 2, ddi};
+  Dual F[EPG_MAXK], Fb[EPG_MAXK], Z[EPG_MAXK];
+  auto dot = [](const double *u, const double *du, const Dual &x, const Dual &y, const Dual &z) -> Dual {
+    Dual r;
+    r.v = u[0] * x.v + u[1] * y.v + u[2] * z.v;
+    r.d = (du[0] * x.v + du[1] * y.v + du[2] * z.v) + (u[0] * x.d + u[1] * y.d + u[2] * z.d);
+    return r;
+  };
+  auto emit = [&](int i, const Dual &x) {
+    dc[i * out_stride] = fabs(x.v);
+    ddc[i * out_stride] = signbit(x.v) ? -x.d : x.d;
+  };
+  const double m0 = sh, dm0 = dsh;
+  F[1] = {b1 * m0, db1 * m0 + b1 * dm0}, Fb[1] = {0, 0}, Z[1] = {-c1 * m0 / 2, -(dc1 * m0 + c1 * dm0) / 2};
+  F[2] = {a1 * m0, da1 * m0 + a1 * dm0}, Fb[2] = {0, 0}, Z[2] = {0, 0};
+  emit(0, F[1]);
+  for (int i = 2; i <= ETL - 1; i++) {
+    const bool first_half = (i <= ETL / 2);
+    const int nproc = first_half ? i : ETL - i + 1;
+    Dual FM = dot(Fv, dFv, F[1], Fb[1], Z[1]), FbM = dot(Fbv, dFbv, F[1], Fb[1], Z[1]), ZM = dot(Zv, dZv, F[1], Fb[1], Z[1]);
+    emit(i - 1, FbM);
+    F[1] = FbM, Z[1] = ZM;
+    Dual pend = FM;
+    for (int j = 2; j <= nproc; j++) {
+      FM = dot(Fv, dFv, F[j], Fb[j], Z[j]), FbM = dot(Fbv, dFbv, F[j], Fb[j], Z[j]), ZM = dot(Zv, dZv, F[j], Fb[j], Z[j]);
+      F[j] = pend;
+      pend = FM;
+      Fb[j - 1] = FbM;
+      Z[j] = ZM;
+    }
+    if (first_half) F[nproc + 1] = pend, Fb[nproc] = {0, 0}, Fb[nproc + 1] = {0, 0}, Z[nproc + 1] = {0, 0};
+  }
+  emit(ETL - 1, dot(Fbv, dFbv, F[1], Fb[1], Z[1]));
+}
+
 struct SetupParams {
   int nTE, nT2, nA, ld, copy_elems;
-  double E1;
+  double E1, refcon;
   double angles[DECAES_MAX_ANGLES];
   double E2[DECAES_MAX_NT2];
   double *basis_rm, *basis_cm, *dbasis_cm;
@@ -106,7 +164,8 @@ __global__ void basis_setup_kernel(const __grid_constant__ SetupParams S) {
   int k = t / S.nT2, j = t % S.nT2;
   double *dc = S.basis_cm + ((size_t)k * S.nT2 + j) * S.nTE;
   double *ddc = S.dbasis_cm + ((size_t)k * S.nT2 + j) * S.nTE;
-  epg_curve_jac(S.nTE, S.angles[k], S.E1, S.E2[j], dc, ddc, 1);
+  if (S.refcon == 180.0) epg_curve_jac(S.nTE, S.angles[k], S.E1, S.E2[j], dc, ddc, 1);  // dispatch of src/T2mapSEcorr.jl:616-620
+  else epg_curve_beta_jac(S.nTE, S.angles[k], S.refcon, S.E1, S.E2[j], dc, ddc, 1);
   double *rm = S.basis_rm + (size_t)k * S.copy_elems;
   for (int i = 0; i < S.nTE; i++) rm[i * S.ld + j] = dc[i];
   if (j == 0) {  // zero the padding so the bulk copy never moves uninitialised bytes
@@ -371,7 +430,6 @@ static int validate_map(const decaes_t2map_opts *o) {
   if (!std::isnan(o->SetFlipAngle) && !(0.0 <= o->SetFlipAngle && o->SetFlipAngle <= 180.0))
     return fail(DECAES_EINVAL, "Fixed flip angle must be in the range [0, 180]");
   if (o->legacy) return fail(DECAES_EUNSUPPORTED, "legacy = true is outside the accelerated path");
-  if (o->RefConAngle != 180.0) return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 is not accelerated yet");
   if (o->nT2 > DECAES_MAX_NT2) return fail(DECAES_EUNSUPPORTED, "nT2 > %d is not supported", DECAES_MAX_NT2);
   if (o->nRefAngles > DECAES_MAX_ANGLES) return fail(DECAES_EUNSUPPORTED, "nRefAngles > %d is not supported", DECAES_MAX_ANGLES);
   if (o->nTE > 72) return fail(DECAES_EUNSUPPORTED, "nTE > 72 is not supported");
@@ -575,6 +633,10 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   // the solver block + search caches (everything in front of the voxel's signal) are idle while the basis is built
   P.epg_smem = P.gram && 3 * P.epg_kmax * 32 <= L.bd;
   if (const char *e = getenv("DECAES_EPG_SMEM")) P.epg_smem = P.epg_smem && atoi(e);
+  P.refcon = o->RefConAngle;
+  if (P.refcon != 180.0 && !fixed && !(P.gram && 3 * P.epg_kmax * 32 <= L.bd))
+    return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 needs the Gram solver and %d bytes of shared EPG scratch per warp", 3 * P.epg_kmax * 32 * 8);
+  if (P.refcon != 180.0) P.epg_smem = 1;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
   if ((size_t)plan->smem_bytes > prop.sharedMemPerBlockOptin)
@@ -618,7 +680,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.basis_rm = ws.basis_rm, P.basis_cm = ws.basis_cm, P.dbasis_cm = ws.dbasis_cm;
   P.scratch = ws.scratch, P.counters = ws.counters;
 
-  S.nTE = nTE, S.nT2 = nT2, S.nA = nA, S.ld = P.ld, S.copy_elems = P.copy_elems, S.E1 = P.E1;
+  S.nTE = nTE, S.nT2 = nT2, S.nA = nA, S.ld = P.ld, S.copy_elems = P.copy_elems, S.E1 = P.E1, S.refcon = o->RefConAngle;
   memcpy(S.angles, P.angles, sizeof S.angles);
   memcpy(S.E2, P.E2, sizeof S.E2);
   S.basis_rm = ws.basis_rm, S.basis_cm = ws.basis_cm, S.dbasis_cm = ws.dbasis_cm;

@@ -23,7 +23,7 @@ struct PipeParams {
   int epg_kmax;         // highest phase state index + 2
   int has_part, sp_lo, sp_hi, mp_lo, mp_hi, has_sigmoid;
   int8_t seeds[DECAES_MAX_ANGLES];
-  double TE, T1, Threshold, Chi2Factor, NoiseLevel, SetFlipAngle, E1;
+  double TE, T1, Threshold, Chi2Factor, NoiseLevel, SetFlipAngle, E1, refcon;
   // volume
   const double *image;
   long long nvox, stride;
@@ -314,7 +314,8 @@ struct Warp {
   __device__ void basis_at(double alpha, long long v) {
     if constexpr (GRAM) {
       PROF_BEGIN(7);
-      if (cP.epg_smem) epg_basis(alpha, v, V);  // lane <-> T2 component, states in the (idle) solver block
+      if (cP.refcon != 180.0) epg_basis_beta(alpha, v, V);
+      else if (cP.epg_smem) epg_basis(alpha, v, V);  // lane <-> T2 component, states in the (idle) solver block
       else if (cP.nTE <= 63) epg_basis_shfl<false>(alpha, v);
       else epg_basis_shfl<true>(alpha, v);
       PROF_END(7);
@@ -458,6 +459,80 @@ struct Warp {
         int i = k % ETL, jj = k / ETL;
         cP.decaybasis[v + (long long)k * cP.stride] = pr[i * ld + jj];
       }
+    }
+    __threadfence_block();
+    __syncwarp();
+  }
+
+  // EPG basis at `alpha` for RefConAngle != 180 (src/EPGdecaycurve.jl:722-818): first refocusing pulse
+  // alpha, later pulses alpha * beta / 180.  lane <-> T2 component, phase states in shared memory,
+  // updated in place (each old state M_j yields F.M_j -> new F_{j+1}, Fbar.M_j -> new Fbar_{j-1},
+  // Z.M_j -> new Z_j); dot products in the reference's order.
+  __device__ __noinline__ void epg_basis_beta(double alpha_deg, long long v, double *S /* [3][K][32] shared scratch */) {
+    const int lane = this->lane;
+    SH(S);
+    const int ETL = cP.nTE, n = cP.nT2, ld = cP.ld;
+    const int K = cP.epg_kmax;
+    double *pr = g + sl.pristine, *pc = g + sl.pristine_cm;
+    GL(pr);
+    GL(pc);
+    const double kk = 0.017453292519943295;
+    const double A = alpha_deg / 180;
+    double sh, ch, sini, cosi;
+    sincos(__dmul_rn(__dmul_rn(A, 180.0), kk) / 2, &sh, &ch);
+    sincos(__dmul_rn(__dmul_rn(A, cP.refcon), kk), &sini, &cosi);
+    const double s2h = __dmul_rn(sh, sh), c2h = __dmul_rn(ch, ch), sin1 = __dmul_rn(__dmul_rn(2.0, sh), ch);
+    const double c2hi = (1 + cosi) / 2, s2hi = 1 - c2hi;
+    const double E1 = cP.E1, m0 = sh;
+#define ST(c, k) S[((c)*K + (k)) * 32 + lane]
+#define DOT3(u0, u1, u2) __dadd_rn(__dadd_rn(__dmul_rn(u0, mF), __dmul_rn(u1, mFb)), __dmul_rn(u2, mZ))
+    _Pragma("unroll 1") for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const bool act = j < n;
+      const double E2 = act ? cP.E2[j] : 0.0;
+      const double E2sq = __dmul_rn(E2, E2), E1E2 = __dmul_rn(E1, E2);
+      const double a1 = __dmul_rn(E2sq, c2h), b1 = __dmul_rn(E2sq, s2h), c1 = __dmul_rn(E1E2, sin1);
+      const double ai = __dmul_rn(E2sq, c2hi), bi = __dmul_rn(E2sq, s2hi), ci = __dmul_rn(E1E2, sini);
+      const double di = __dmul_rn(__dmul_rn(E1, E1), cosi), hci = ci / 2;
+      double mF, mFb, mZ, FM, FbM, ZM;
+      ST(0, 1) = __dmul_rn(b1, m0), ST(1, 1) = 0.0, ST(2, 1) = __dmul_rn(-c1, m0) / 2;
+      ST(0, 2) = __dmul_rn(a1, m0), ST(1, 2) = 0.0, ST(2, 2) = 0.0;
+      if (act) {
+        const double val = fabs(__dmul_rn(b1, m0));
+        pr[j] = val, pc[j * ETL] = val;
+      }
+      _Pragma("unroll 1") for (int i = 2; i <= ETL - 1; i++) {
+        const bool first_half = (i <= ETL / 2);
+        const int nproc = first_half ? i : ETL - i + 1;
+        mF = ST(0, 1), mFb = ST(1, 1), mZ = ST(2, 1);
+        FM = DOT3(ai, bi, ci), FbM = DOT3(bi, ai, -ci), ZM = DOT3(-hci, hci, di);
+        if (act) {
+          const double val = fabs(FbM);
+          pr[(i - 1) * ld + j] = val, pc[j * ETL + i - 1] = val;
+        }
+        ST(0, 1) = FbM, ST(2, 1) = ZM;
+        double pend = FM;
+        _Pragma("unroll 1") for (int k = 2; k <= nproc; k++) {
+          mF = ST(0, k), mFb = ST(1, k), mZ = ST(2, k);
+          FM = DOT3(ai, bi, ci), FbM = DOT3(bi, ai, -ci), ZM = DOT3(-hci, hci, di);
+          ST(0, k) = pend;
+          pend = FM;
+          ST(1, k - 1) = FbM;
+          ST(2, k) = ZM;
+        }
+        if (first_half) ST(0, nproc + 1) = pend, ST(1, nproc) = 0.0, ST(1, nproc + 1) = 0.0, ST(2, nproc + 1) = 0.0;
+      }
+      mF = ST(0, 1), mFb = ST(1, 1), mZ = ST(2, 1);
+      if (act) {
+        const double val = fabs(DOT3(bi, ai, -ci));
+        pr[(ETL - 1) * ld + j] = val, pc[j * ETL + ETL - 1] = val;
+      }
+    }
+#undef ST
+#undef DOT3
+    __syncwarp();
+    if (cP.decaybasis && !cP.fixed_alpha) {
+      _Pragma("unroll 1") for (int k = lane; k < ETL * n; k += 32) cP.decaybasis[v + (long long)k * cP.stride] = pc[k];
     }
     __threadfence_block();
     __syncwarp();

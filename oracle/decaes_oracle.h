@@ -46,6 +46,9 @@ void orc_epg_decay_curve_jac(int ETL, double alpha_deg, double TE, double T2, do
 /* general RefConAngle variant: :722-818.  work: 6*ETL doubles */
 void orc_epg_decay_curve_beta(int ETL, double alpha_deg, double TE, double T2, double T1,
                               double beta_deg, double *dc, double *work);
+/* value + d/dalpha (per degree) of the general variant, forward mode.  work: 12*ETL doubles */
+void orc_epg_decay_curve_beta_jac(int ETL, double alpha_deg, double TE, double T2, double T1,
+                                  double beta_deg, double *dc, double *ddc, double *work);
 double orc_sind(double x);
 
 /* ---------- NNLS (src/NNLS.jl, src/lsqnonneg.jl:5-164) ---------- */

@@ -286,3 +286,75 @@ void orc_epg_decay_curve_beta(int ETL, double alpha_deg, double TE, double T2, d
 #undef V2
 #undef SET
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Value + d/dalpha (per degree) of the general-beta curve: hand forward mode through the same
+ * recursion (the reference differentiates it with ForwardDiff, src/EPGdecaycurve.jl:224-248).
+ * In-place state update: old state M_j yields F.M_j -> new F_{j+1}, Fbar.M_j -> new Fbar_{j-1},
+ * Z.M_j -> new Z_j, which is the double-buffered update of :722-818 with the buffers merged
+ * (values are bitwise those of orc_epg_decay_curve_beta; tests/test_oracle_epg.py).
+ * work: 12*ETL doubles.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  double v, d;
+} dual_t;
+static inline dual_t ddot3(const double *u, const double *du, dual_t x, dual_t y, dual_t z) {
+  dual_t r;
+  r.v = u[0] * x.v + u[1] * y.v + u[2] * z.v;
+  r.d = (du[0] * x.v + du[1] * y.v + du[2] * z.v) + (u[0] * x.d + u[1] * y.d + u[2] * z.d);
+  return r;
+}
+void orc_epg_decay_curve_beta_jac(int ETL, double alpha_deg, double TE, double T2, double T1,
+                                  double beta_deg, double *dc, double *ddc, double *work) {
+  const double kk = ORC_PI / 180.0;
+  const double A = alpha_deg / 180;
+  const double a1r = (A * 180) * kk, air = (A * beta_deg) * kk;
+  const double kb = (beta_deg / 180) * kk;
+  const double E1 = exp(-(TE / 2) / T1), E2 = exp(-(TE / 2) / T2);
+  double sh, ch, sini, cosi;
+  sincos(a1r / 2, &sh, &ch);
+  sincos(air, &sini, &cosi);
+  const double dsh = ch * (kk / 2), dch = -sh * (kk / 2);
+  const double s2h = sh * sh, c2h = ch * ch, ds2h = 2 * sh * dsh, dc2h = 2 * ch * dch;
+  const double sin1 = 2 * sh * ch, dsin1 = 2 * (dsh * ch + sh * dch);
+  const double dsini = cosi * kb, dcosi = -sini * kb;
+  const double c2hi = (1 + cosi) / 2, s2hi = 1 - c2hi, dc2hi = dcosi / 2, ds2hi = -dc2hi;
+  const double E2sq = E2 * E2, E1E2 = E1 * E2, E1sq = E1 * E1;
+  const double a1 = E2sq * c2h, b1 = E2sq * s2h, c1 = E1E2 * sin1;
+  const double da1 = E2sq * dc2h, db1 = E2sq * ds2h, dc1 = E1E2 * dsin1;
+  const double ai = E2sq * c2hi, bi = E2sq * s2hi, ci = E1E2 * sini, di = E1sq * cosi;
+  const double dai = E2sq * dc2hi, dbi = E2sq * ds2hi, dci = E1E2 * dsini, ddi = E1sq * dcosi;
+  const double Fv[3] = {ai, bi, ci}, Fbv[3] = {bi, ai, -ci}, Zv[3] = {-ci / 2, ci / 2, di};
+  const double dFv[3] = {dai, dbi, dci}, dFbv[3] = {dbi, dai, -dci}, dZv[3] = {-dci / 2, dci / 2, ddi};
+  dual_t *F = (dual_t *)work, *Fb = F + ETL, *Z = Fb + ETL; /* 1-based use, ETL/2 + 2 entries needed */
+  const dual_t zero = {0.0, 0.0};
+  const double m0 = sh, dm0 = dsh;
+#define EMIT(i, x) (dc[i] = fabs((x).v), ddc[i] = signbit((x).v) ? -(x).d : (x).d)
+  F[1].v = b1 * m0, F[1].d = db1 * m0 + b1 * dm0, Fb[1] = zero;
+  Z[1].v = -c1 * m0 / 2, Z[1].d = -(dc1 * m0 + c1 * dm0) / 2;
+  F[2].v = a1 * m0, F[2].d = da1 * m0 + a1 * dm0, Fb[2] = zero, Z[2] = zero;
+  EMIT(0, F[1]);
+  for (int i = 2; i <= ETL - 1; i++) {
+    const int first_half = (i <= ETL / 2);
+    const int nproc = first_half ? i : ETL - i + 1;
+    dual_t FM = ddot3(Fv, dFv, F[1], Fb[1], Z[1]), FbM = ddot3(Fbv, dFbv, F[1], Fb[1], Z[1]),
+           ZM = ddot3(Zv, dZv, F[1], Fb[1], Z[1]);
+    EMIT(i - 1, FbM);
+    F[1] = FbM, Z[1] = ZM;
+    dual_t pend = FM;
+    for (int j = 2; j <= nproc; j++) {
+      FM = ddot3(Fv, dFv, F[j], Fb[j], Z[j]), FbM = ddot3(Fbv, dFbv, F[j], Fb[j], Z[j]),
+      ZM = ddot3(Zv, dZv, F[j], Fb[j], Z[j]);
+      F[j] = pend;
+      pend = FM;
+      Fb[j - 1] = FbM;
+      Z[j] = ZM;
+    }
+    if (first_half) F[nproc + 1] = pend, Fb[nproc] = zero, Fb[nproc + 1] = zero, Z[nproc + 1] = zero;
+  }
+  {
+    dual_t last = ddot3(Fbv, dFbv, F[1], Fb[1], Z[1]);
+    EMIT(ETL - 1, last);
+  }
+#undef EMIT
+}

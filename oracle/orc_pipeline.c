@@ -111,14 +111,9 @@ int orc_setup_tables(const decaes_t2map_opts *o, double *echotimes, double *t2ti
         if (o->RefConAngle == 180.0) {
           orc_epg_decay_curve_jac(nTE, ang[k], o->TE, T2[j], o->T1, dc, ddc, work);
         } else {
-          /* beta != 180: value from the general kernel; derivative by central difference of it
-           * (only used by the surrogate gradient; the reference differentiates with ForwardDiff) */
-          const double h = 1e-6;
-          double *dp = ddc, *dm = work + 6 * nTE;
-          orc_epg_decay_curve_beta(nTE, ang[k] + h, o->TE, T2[j], o->T1, o->RefConAngle, dp, work);
-          orc_epg_decay_curve_beta(nTE, ang[k] - h, o->TE, T2[j], o->T1, o->RefConAngle, dm, work);
-          for (int i = 0; i < nTE; i++) ddc[i] = (dp[i] - dm[i]) / (2 * h);
-          orc_epg_decay_curve_beta(nTE, ang[k], o->TE, T2[j], o->T1, o->RefConAngle, dc, work);
+          /* beta != 180: general kernel :722-818, differentiated in forward mode like the reference's
+           * ForwardDiff pass (src/T2mapSEcorr.jl:299-308) */
+          orc_epg_decay_curve_beta_jac(nTE, ang[k], o->TE, T2[j], o->T1, o->RefConAngle, dc, ddc, work);
         }
         size_t off = ((size_t)k * nT2 + j) * nTE;
         if (basis) memcpy(basis + off, dc, sizeof(double) * nTE);

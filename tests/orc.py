@@ -130,6 +130,7 @@ def lib():
         L.orc_linrange.argtypes = [C.c_double, C.c_double, C.c_int, dp]
         L.orc_epg_decay_curve.argtypes = [C.c_int] + [C.c_double] * 4 + [dp, dp]
         L.orc_epg_decay_curve_jac.argtypes = [C.c_int] + [C.c_double] * 4 + [dp, dp, dp]
+        L.orc_epg_decay_curve_beta_jac.argtypes = [C.c_int] + [C.c_double] * 5 + [dp, dp, dp]
         L.orc_epg_decay_curve_beta.argtypes = [C.c_int] + [C.c_double] * 5 + [dp, dp]
         L.orc_svdvals.argtypes = [C.c_int, C.c_int, dp, C.c_int, dp, dp]
         L.orc_solve_triangular.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int]
@@ -167,6 +168,13 @@ def epg(ETL, alpha, TE, T2, T1, beta=None):
         lib().orc_epg_decay_curve_beta(ETL, C.c_double(alpha), C.c_double(TE), C.c_double(T2), C.c_double(T1),
                                        C.c_double(beta), _p(dc), _p(work))
     return dc
+
+
+def epg_beta_jac(ETL, alpha, TE, T2, T1, beta):
+    dc, ddc, work = np.zeros(ETL), np.zeros(ETL), np.zeros(12 * ETL)
+    lib().orc_epg_decay_curve_beta_jac(ETL, C.c_double(alpha), C.c_double(TE), C.c_double(T2), C.c_double(T1),
+                                       C.c_double(beta), _p(dc), _p(ddc), _p(work))
+    return dc, ddc
 
 
 def epg_jac(ETL, alpha, TE, T2, T1):

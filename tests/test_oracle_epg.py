@@ -116,3 +116,19 @@ def test_sind_exact_cases(orc):
     assert L.orc_sind(30.0) == pytest.approx(0.5, abs=1e-16)
     assert L.orc_sind(180.0) == 0.0
     assert L.orc_sind(45.0) == pytest.approx(np.sqrt(0.5), abs=1.2e-16)
+
+
+@pytest.mark.parametrize("ETL", [4, 5, 8, 17, 32, 56, 64])
+@pytest.mark.parametrize("beta", [90.0, 120.0, 150.0, 179.0])
+def test_beta_jacobian_forward_mode(orc, ETL, beta):
+    """Forward-mode Jacobian of the general-beta kernel: values are bitwise those of the double-buffered
+    restatement of src/EPGdecaycurve.jl:722-818, derivatives match central differences
+    (the reference's own check of its ForwardDiff pass, test/epg.jl:161-172)."""
+    rng = np.random.default_rng(ETL)
+    for _ in range(5):
+        alpha, T2 = rng.uniform(50, 180), rng.uniform(0.01, 2.0)
+        dc, ddc = orc.epg_beta_jac(ETL, alpha, 10e-3, T2, 1.0, beta)
+        np.testing.assert_array_equal(dc, orc.epg(ETL, alpha, 10e-3, T2, 1.0, beta=beta))
+        h = 1e-5
+        fd = (orc.epg(ETL, alpha + h, 10e-3, T2, 1.0, beta=beta) - orc.epg(ETL, alpha - h, 10e-3, T2, 1.0, beta=beta)) / (2 * h)
+        np.testing.assert_allclose(ddc, fd, rtol=2e-6, atol=1e-9)
