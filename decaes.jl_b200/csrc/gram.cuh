@@ -291,6 +291,42 @@ __device__ __forceinline__ void gram_solve_s(double *V, int ld, int k) {
   __syncwarp();
 }
 
+// Remove pivot position imv, then any other non-positive coefficient (first found), compacting P
+// (src/NNLS.jl:735-778); the factorisation follows by Givens downdates (k <= 32) or is rebuilt.
+// Returns the new number of active columns; s is up to date on return.
+__device__ __noinline__ int gram_remove(double *V, int ld, int k, int imv, double mu2) {
+  __builtin_assume(__isShared(V));
+  const int lane = lane_id();
+  int *P = (int *)(V + GV_P);
+  const bool small = k <= 32;
+  while (true) {
+    if (small) gram_downdate(V, ld, k, imv);
+    int pn = 0;
+    if (lane >= imv && lane < k - 1) pn = P[lane + 1];
+    if (lane == 0) V[GV_X + P[imv]] = 0.0;
+    __syncwarp();
+    if (k > 32) {
+      if (lane == 0)
+        for (int t = imv; t < k - 1; t++) P[t] = P[t + 1];
+    } else if (lane >= imv && lane < k - 1) {
+      P[lane] = pn;
+    }
+    __syncwarp();
+    k -= 1;
+    unsigned bad = 0x7fffffffu;
+    _Pragma("unroll 1") for (int t = lane; t < k; t += 32)
+      if (V[GV_X + P[t]] <= 0.0 && (unsigned)t < bad) bad = t;
+    bad = __reduce_min_sync(DECAES_FULL_MASK, bad);
+    if (bad == 0x7fffffffu) break;
+    imv = (int)bad;
+  }
+  if (small) {
+    gram_solve_s(V, ld, k);
+    return k;
+  }
+  return gram_refactor(V, ld, k, mu2);
+}
+
 // Lawson–Hanson main loop.  cold: start from the empty set with the reference's warm dual
 // (src/lsqnonneg.jl:44-70).  warm: start from the feasible point x supported on `mask`.
 __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, int max_set, bool warm, unsigned long long mask) {
@@ -303,6 +339,12 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
   int k = 0, iter = 0;
   const int max_iter = 3 * n;
   bool check_first = false;
+  // the two columns of this lane (n <= 64); out-of-range ones are clamped and never win
+  const int j0 = lane < n ? lane : 0, j1 = lane + 32 < n ? lane + 32 : 0;
+  const bool v0 = lane < n, v1 = lane + 32 < n;
+  unsigned long long key = 0ull;  // this lane's best positive dual (bit pattern) and its column
+  int bj = 0x7fffffff;
+  bool have_pick = false;
 
   if (!warm) {
     mask = 0ull;
@@ -340,13 +382,16 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
     if (!check_first) {
       if (k >= max_set) break;
       // ---- entering column: largest positive dual, first on ties; test its coefficient ----
-      unsigned long long key = 0ull, best;
-      int bj = 0x7fffffff;
-      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
-        const double v = V[GV_W + j];
-        const unsigned long long kb = (unsigned long long)__double_as_longlong(v);
-        if (!((mask >> j) & 1ull) && v > 0.0 && kb > key) key = kb, bj = j;
+      if (!have_pick) {  // duals in shared memory (initial dual, or after a rejection)
+        key = 0ull, bj = 0x7fffffff;
+        _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
+          const double v = V[GV_W + j];
+          const unsigned long long kb = (unsigned long long)__double_as_longlong(v);
+          if (!((mask >> j) & 1ull) && v > 0.0 && kb > key) key = kb, bj = j;
+        }
       }
+      have_pick = false;
+      unsigned long long best;
       bj = warp_argmax_bits(key, bj, best);
       if (best == 0ull) break;  // no positive dual left: KKT point
       if (!gram_append(V, ld, k, bj, mu2, true)) {
@@ -367,7 +412,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
         capped = true;
         break;
       }
-      unsigned long long key = ~0ull, best;
+      unsigned long long fkey = ~0ull, best;
       int imv = 0x7fffffff;
       _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
         const double st = V[GV_S + t];
@@ -375,60 +420,43 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
           const double xi = V[GV_X + P[t]];
           const double tt = ddiv(-xi, st - xi);
           const unsigned long long kb = (unsigned long long)__double_as_longlong(tt);
-          if (tt < 2.0 && kb < key) key = kb, imv = t;  // tt >= 0 here, so the bit pattern orders like the value
+          if (tt < 2.0 && kb < fkey) fkey = kb, imv = t;  // tt >= 0 here, so the bit pattern orders like the value
         }
       }
-      if (__all_sync(DECAES_FULL_MASK, key == ~0ull)) break;  // all coefficients feasible
-      imv = warp_argmin_bits(key, imv, best);
+      if (__all_sync(DECAES_FULL_MASK, fkey == ~0ull)) break;  // all coefficients feasible
+      imv = warp_argmin_bits(fkey, imv, best);
       const double al = __longlong_as_double((long long)best);
       _Pragma("unroll 1") for (int t = lane; t < k; t += 32) {
         const int jx = P[t];
         V[GV_X + jx] = fma(al, V[GV_S + t] - V[GV_X + jx], V[GV_X + jx]);
       }
       __syncwarp();
-      // remove imv, then any other non-positive coefficient (first found), compacting P
-      const bool small = k <= 32;
-      while (true) {
-        if (small) gram_downdate(V, ld, k, imv);
-        int pn = 0;
-        if (lane >= imv && lane < k - 1) pn = P[lane + 1];
-        if (lane == 0) V[GV_X + P[imv]] = 0.0;
-        __syncwarp();
-        if (k > 32) {
-          if (lane == 0)
-            for (int t = imv; t < k - 1; t++) P[t] = P[t + 1];
-        } else if (lane >= imv && lane < k - 1) {
-          P[lane] = pn;
-        }
-        __syncwarp();
-        k -= 1;
-        unsigned bad = 0x7fffffffu;
-        _Pragma("unroll 1") for (int t = lane; t < k; t += 32)
-          if (V[GV_X + P[t]] <= 0.0 && (unsigned)t < bad) bad = t;
-        bad = __reduce_min_sync(DECAES_FULL_MASK, bad);
-        if (bad == 0x7fffffffu) break;
-        imv = (int)bad;
-      }
-      if (small) {
-        gram_solve_s(V, ld, k);
-        mask = mask_of(P, k);
-        continue;
-      }
-      k = gram_refactor(V, ld, k, mu2);
+      k = gram_remove(V, ld, k, imv, mu2);
       mask = mask_of(P, k);
     }
     if (capped) break;
 
     _Pragma("unroll 1") for (int t = lane; t < k; t += 32) V[GV_X + P[t]] = V[GV_S + t];
     __syncwarp();
-    // ---- dual: w_j = c_j - sum_t G(P[t], j) s_t, zero on the active set ----
+    // ---- dual: w_j = c_j - sum_t G(P[t], j) s_t, zero on the active set; both columns of the lane
+    //      advance together and the lane's candidate for the next pivot is picked on the fly ----
     {
       GP_BEGIN();
-      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
-        double a = V[GV_C + j];
-        _Pragma("unroll 4") for (int t = 0; t < k; t++) a = fma(-gram_G(T, ld, P[t], j), V[GV_S + t], a);
-        V[GV_W + j] = ((mask >> j) & 1ull) ? 0.0 : a;
+      double a0 = V[GV_C + j0], a1 = V[GV_C + j1];
+      _Pragma("unroll 4") for (int t = 0; t < k; t++) {
+        const int pt = P[t];
+        const double st = V[GV_S + t];
+        a0 = fma(-gram_G(T, ld, pt, j0), st, a0);
+        a1 = fma(-gram_G(T, ld, pt, j1), st, a1);
       }
+      if (!v0 || ((mask >> j0) & 1ull)) a0 = 0.0;
+      if (!v1 || ((mask >> j1) & 1ull)) a1 = 0.0;
+      if (v0) V[GV_W + j0] = a0;
+      if (v1) V[GV_W + j1] = a1;
+      const unsigned long long k0 = a0 > 0.0 ? (unsigned long long)__double_as_longlong(a0) : 0ull;
+      const unsigned long long k1 = a1 > 0.0 ? (unsigned long long)__double_as_longlong(a1) : 0ull;
+      key = k1 > k0 ? k1 : k0, bj = k1 > k0 ? j1 : (k0 ? j0 : 0x7fffffff);
+      have_pick = true;
       __syncwarp();
       GP_END(2);
     }

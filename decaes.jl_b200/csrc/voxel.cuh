@@ -395,7 +395,9 @@ struct Warp {
     sincos(alpha_deg * 0.017453292519943295, &sina, &cosa);
     const double m0 = sind_0_180(alpha_deg / 2);
     const double E1 = cP.E1;
-#define ST(c, k) S[((c)*K + (k)) * 32 + lane]
+    // the three state arrays never alias: lets the compiler overlap the loads of one state with the stores of the previous one
+    double *__restrict__ const sF = S + lane, *__restrict__ const sB = S + K * 32 + lane, *__restrict__ const sZ = S + 2 * K * 32 + lane;
+#define ST(c, k) ((c) == 0 ? sF : (c) == 1 ? sB : sZ)[(k) * 32]
     for (int j0 = 0; j0 < n; j0 += 32) {
       const int j = j0 + lane;
       const bool act = j < n;
@@ -430,7 +432,7 @@ struct Warp {
         }
         ST(0, 1) = vFb, ST(2, 1) = vZ;
         double pend = vF;
-        for (int k = 2; k <= kmax; k++) {
+        _Pragma("unroll 1") for (int k = 2; k <= kmax; k++) {
           F = ST(0, k), Fb = ST(1, k), Z = ST(2, k);
           ST(0, k) = pend;
           UPD();
