@@ -547,6 +547,9 @@ struct DeviceWs {
   double *basis_rm = nullptr, *basis_cm = nullptr, *dbasis_cm = nullptr, *scratch = nullptr, *gram_set = nullptr;
   unsigned long long *counters = nullptr;
   size_t basis_rm_cap = 0, basis_cm_cap = 0, scratch_cap = 0, gram_cap = 0;
+  size_t l2_persist_max = 0, l2_window_max = 0;  // persisting-L2 carve-out set aside for the scratch, largest access-policy window
+  bool props_known = false;
+  cudaDeviceProp prop;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_pending = false;
   int sm_count = 0;
@@ -637,8 +640,22 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if (P.refcon != 180.0 && !fixed && !(P.gram && 3 * P.epg_kmax * 32 <= L.bd))
     return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 needs the Gram solver and %d bytes of shared EPG scratch per warp", 3 * P.epg_kmax * 32 * 8);
   if (P.refcon != 180.0) P.epg_smem = 1;
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  {
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    DeviceWs &w0 = g_ws[dev];
+    if (!w0.props_known) {  // cudaGetDeviceProperties is slow (milliseconds): once per device
+      CUDA_TRY(cudaGetDeviceProperties(&w0.prop, dev));
+      w0.props_known = true;
+      if (w0.prop.persistingL2CacheMaxSize > 0 &&
+          cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)w0.prop.persistingL2CacheMaxSize) == cudaSuccess) {
+        w0.l2_persist_max = (size_t)w0.prop.persistingL2CacheMaxSize;
+        w0.l2_window_max = (size_t)w0.prop.accessPolicyMaxWindowSize;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
+  const cudaDeviceProp &prop = g_ws[dev].prop;
   if ((size_t)plan->smem_bytes > prop.sharedMemPerBlockOptin)
     return fail(DECAES_EUNSUPPORTED, "problem needs %d bytes of shared memory per warp (> %zu)", plan->smem_bytes,
                 prop.sharedMemPerBlockOptin);
@@ -721,11 +738,32 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
   int64_t ngroups = (nvox + DECAES_GROUP - 1) / DECAES_GROUP;
   int grid = (int)std::min<int64_t>(plan.grid, std::max<int64_t>((ngroups + plan.warps_per_cta - 1) / plan.warps_per_cta, 1));
   CUDA_TRY(cudaMemcpyToSymbolAsync(cP, &P, sizeof(PipeParams), 0, cudaMemcpyHostToDevice, stream));
+  // Keep the per-warp scratch (the voxel's basis in both layouts, ~46 KB per warp, rewritten for every voxel)
+  // resident in L2: without the window the streaming image / output traffic evicts it and every basis is
+  // written back to and re-read from HBM (ncu: 19 KB of DRAM writes per voxel).
+  const size_t scratch_bytes = (size_t)plan.grid * plan.warps_per_cta * P.scratch_per_warp * sizeof(double);
+  bool window = ws.l2_persist_max > 0 && ws.l2_window_max > 0 && !getenv("DECAES_NO_L2_WINDOW");
+  if (window) {
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.base_ptr = (void *)ws.scratch;
+    attr.accessPolicyWindow.num_bytes = std::min(scratch_bytes, ws.l2_window_max);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ws.l2_persist_max / (double)attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    window = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+    if (!window) cudaGetLastError();
+  }
   if (P.gram)
     voxel_pipeline_kernel<true><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
   else
     voxel_pipeline_kernel<false><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
+  if (window) {
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);  // later work on this stream: default policy
+  }
   CUDA_TRY(cudaEventRecord(ws.ev[2], stream));
   ws.ev_pending = true;
   return DECAES_OK;

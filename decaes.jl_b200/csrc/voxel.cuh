@@ -396,7 +396,7 @@ struct Warp {
     const double m0 = sind_0_180(alpha_deg / 2);
     const double E1 = cP.E1;
     // the three state arrays never alias: lets the compiler overlap the loads of one state with the stores of the previous one
-    double *__restrict__ const sF = S + lane, *__restrict__ const sB = S + K * 32 + lane, *__restrict__ const sZ = S + 2 * K * 32 + lane;
+    double *const sF = S + lane, *const sB = S + K * 32 + lane, *const sZ = S + 2 * K * 32 + lane;
 #define ST(c, k) ((c) == 0 ? sF : (c) == 1 ? sB : sZ)[(k) * 32]
     for (int j0 = 0; j0 < n; j0 += 32) {
       const int j = j0 + lane;
