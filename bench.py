@@ -250,10 +250,19 @@ def main():
         peak = pkg.measure_fp64_peak()
         mean_kernel_s = 1e-3 * sum(kernel_ms) / max(len(kernel_ms), 1)
         roofline = None
+        # DRAM traffic of the pipeline kernel: measured once per round with ncu (profiles/r01_traffic.json,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch), scaled to this launch's voxel count
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and args.workload == "cfg3":
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["voxels"] * nvox
         if flops_per_voxel:
             achieved = flops_per_voxel * nvox / mean_kernel_s
             roofline = {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
-                        "frac": achieved / peak, "traffic": None,
+                        "frac": achieved / peak, "traffic": traffic,
+                        "traffic_source": "ncu capture committed as profiles/r01_traffic.json (bytes per launch, scaled by voxels)",
                         "peak_source": "measured in this run by decaes_measure_fp64_peak (independent DFMA chains on all SMs); MEASURED_PEAKS.json has no FP64 entry",
                         "flops_per_voxel": flops_per_voxel, "kernel": "voxel_pipeline_kernel",
                         "kernel_ms": 1e3 * mean_kernel_s,
@@ -266,7 +275,7 @@ def main():
             "config": {"workload": f"{args.workload}: {nTE}-echo {'x'.join(map(str, shape))}, nT2={nT2}, Reg={Reg} (+fused T2part), one volume per rank",
                        "voxels_per_rank": nvox, "l2": "inputs+outputs per step exceed L2 (no flush needed)",
                        "debug_voxels_override": bool(args.voxels)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * args.steps,  # basis_setup + gram_setup + voxel_pipeline per step
             "kernel_ms_per_step": sum(kernel_ms) / max(len(kernel_ms), 1),
             "roofline": roofline, "cpu_baseline": cpu,
             "voxels_processed_last_step": processed, "checksum_gdn": checksum,
