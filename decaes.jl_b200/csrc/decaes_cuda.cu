@@ -598,7 +598,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.sync_mask = 3;
   P.sync_groups = 1;
   if (const char *e = getenv("DECAES_SYNC_GROUPS")) P.sync_groups = std::max(1, atoi(e));
-  P.fa_warm = 1;
+  P.fa_warm = 4;
   if (const char *e = getenv("DECAES_FA_WARM")) P.fa_warm = atoi(e);
   if (const char *e = getenv("DECAES_SYNC_MASK")) P.sync_mask = atoi(e);
   P.ldg = (nT2 + 1) | 1;  // one array holds the lower triangle of G and, above it, M = L^-1 (gram.cuh)
@@ -807,6 +807,13 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
               100.0 * kh[5 * w] / std::max<double>(1, (double)gp[4 + w]), 100.0 * kh[5 * w + 1] / std::max<double>(1, (double)gp[4 + w]),
               100.0 * kh[5 * w + 2] / std::max<double>(1, (double)gp[4 + w]), 100.0 * kh[5 * w + 3] / std::max<double>(1, (double)gp[4 + w]),
               100.0 * kh[5 * w + 4] / std::max<double>(1, (double)gp[4 + w]));
+    unsigned long long sh[3][48];
+    cudaMemcpyFromSymbol(sh, g_solve_hist, sizeof sh);
+    fprintf(stderr, "  solve # (0-27 Tikhonov, 28+ unregularised): calls/voxel, appends/solve, inner iterations/solve\n");
+    for (int i = 0; i < 48; i++)
+      if (sh[0][i]) fprintf(stderr, "   %2d: %.3f  %.2f  %.2f\n", i, sh[0][i] / nv, (double)sh[1][i] / sh[0][i], (double)sh[2][i] / sh[0][i]);
+    static unsigned long long zz[3][48];
+    cudaMemcpyToSymbol(g_solve_hist, zz, sizeof zz);
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(g_prof, z, sizeof z);
     cudaMemcpyToSymbol(g_khist, z, sizeof kh);

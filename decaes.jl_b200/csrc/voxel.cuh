@@ -37,7 +37,7 @@ struct PipeParams {
   const double *gram_set;   // [nA][nT2*ldg]     A_k'A_k per grid angle (Gram solver)
   int gram, ldg;            // solver variant (1 = normal-equation active set), leading dimension of G
   int warps_per_cta, smem_per_warp;  // CTA shape: bytes of dynamic shared memory owned by each warp
-  int fa_warm;              // warm-start flip-angle probes from the nearest probed angle (Gram solver)
+  int fa_warm;              // warm-start flip-angle probes from a probed angle at most this many grid steps away (0 = never)
   int sync_groups;          // 1: CTA-wide phase barriers; g > 1: one barrier per group of warps (warp id mod g)
   int sync_mask;            // which intra-round CTA barriers are active (bit 0: after flip angle, bit 1: after basis)
   int epg_smem;             // EPG at the fitted angle keeps its states in shared memory (lane <-> component)
@@ -166,6 +166,7 @@ struct Warp {
   int cur_slot;     // 0-based current cache slot (persists across voxels like work.idx[])
   int lane;
   unsigned long long n_early, n_overflow;
+  int nsolve_voxel = 0, nunreg_voxel = 0;  // Tikhonov / unregularised solves of the current voxel (DECAES_PROFILE)
 
   __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
       : sl(p.nTE, p.nT2, p.copy_elems, p.reg == 2) {
@@ -557,6 +558,7 @@ struct Warp {
 
   // solve!(cache, mu)  src/lsqnonneg.jl:417-444 — exact-mu hit or solve into the next slot
   __device__ void cache_reset() {
+    nsolve_voxel = 0;
     if (lane < DECAES_NCACHE) slot_mu[lane] = CUDART_NAN;
     __syncwarp();
   }
@@ -1138,6 +1140,13 @@ struct Warp {
     }
     PROF_BEGIN(1);
     o = gram_nnls(V, cP.nT2, cP.ldg, 0.0, max_set, warm_mask != 0ull, warm_mask);
+#ifdef DECAES_PROFILE
+    if (lane == 0) {
+      const int si = 28 + (nunreg_voxel < 19 ? nunreg_voxel : 19);
+      atomicAdd(&g_solve_hist[0][si], 1ull), atomicAdd(&g_solve_hist[1][si], (unsigned long long)o.nappend), atomicAdd(&g_solve_hist[2][si], (unsigned long long)o.iters);
+    }
+    nunreg_voxel++;
+#endif
     PROF_END(1);
     PROF_BEGIN(2);
     double r2 = gram_residual(src.Acm, o.k);
@@ -1171,14 +1180,16 @@ struct Warp {
     PROF_BEGIN(0);
     gram_rhs(src.Arm);
     PROF_END(0);
-    // warm start from the active set found at the nearest angle already probed
+    // warm start from the active set found at the nearest angle already probed, if it is close enough:
+    // from a distant angle the inherited set is mostly wrong and costs more removals than the reference's
+    // cold start needs pivots (measured: 17 inner iterations from 63 grid steps away, 7.5 cold, 4.4 from 1 step)
     unsigned long long warm = 0ull;
     if (seen && cP.fa_warm) {
       unsigned long long below = seen & ((1ull << kang) - 1ull), above = seen >> kang;  // bit kang itself is never set
       int jb = below ? 63 - __clzll((long long)below) : -1000;
       int ja = above ? kang + __ffsll((long long)above) - 1 : 1000;
       int jn = (kang - jb <= ja - kang) ? jb : ja;
-      warm = fa_mask_p[jn];
+      if (abs(kang - jn) <= cP.fa_warm) warm = fa_mask_p[jn];
     }
     GramOut o;
     u = gram_solve_unreg(src, o, warm);
@@ -1363,6 +1374,13 @@ struct Warp {
     }
     PROF_BEGIN(9);
     o = gram_nnls(V, n, cP.ldg, mu2, n, nearest >= 0, nearest >= 0 ? slot_mask[nearest] : 0ull);
+#ifdef DECAES_PROFILE
+    if (lane == 0) {
+      const int si = nsolve_voxel < 47 ? nsolve_voxel : 47;
+      atomicAdd(&g_solve_hist[0][si], 1ull), atomicAdd(&g_solve_hist[1][si], (unsigned long long)o.nappend), atomicAdd(&g_solve_hist[2][si], (unsigned long long)o.iters);
+    }
+    nsolve_voxel++;
+#endif
     PROF_END(9);
     PROF_BEGIN(2);
     double r2 = gram_residual(src.Acm, o.k);
@@ -1396,6 +1414,7 @@ struct Warp {
     VIEW(double, bd);
     const int nTE = cP.nTE;
     v_cur = v;
+    nunreg_voxel = 0;
     double mx = 0.0;
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
       double bi = __ldg(signal + (long long)i * cP.stride);
