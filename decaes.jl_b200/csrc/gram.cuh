@@ -37,7 +37,8 @@ namespace decaes {
 // [0..3] cycles append/factor/dual/nnls, [4..7] calls, [8] sum k at append, [9] sum k at factor,
 // [11] warm calls, [12] cold calls, [13] sum final k, [14] sum inner iterations, [15] factor fallbacks
 __device__ unsigned long long g_prof[16];
-__device__ unsigned long long g_khist[2][5];  // k at append / factor: <=4, <=8, <=12, <=16, >16
+__device__ unsigned long long g_khist[2][5];
+__device__ unsigned long long g_solve_hist[3][48];  // per solve index within a voxel (0-27 Tikhonov, 28+ unregularised): calls, appends, inner iterations  // k at append / factor: <=4, <=8, <=12, <=16, >16
 #define GP_BEGIN() long long gp_t0 = clock64()
 #define GP_END(id) if (lane_id() == 0) { atomicAdd(&g_prof[id], (unsigned long long)(clock64() - gp_t0)); atomicAdd(&g_prof[4 + id], 1ull); }
 #define GP_ADD(id, v) if (lane_id() == 0) atomicAdd(&g_prof[id], (unsigned long long)(v))
@@ -55,6 +56,7 @@ struct GramOut {
   int k;                     // number of active columns
   unsigned long long mask;   // active set as a bit mask
   double xnorm_sq;           // sum of squares of the solution
+  int iters, nappend;        // diagnostics (DECAES_PROFILE histograms)
 };
 
 #define GM_(t, u) T[(u) * ld + (t) + 1]
@@ -336,7 +338,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
   int *P = (int *)(V + GV_P);
   GP_BEGIN();
   GP_ADD(warm ? 11 : 12, 1);
-  int k = 0, iter = 0;
+  int k = 0, iter = 0, nappend = 0;
   const int max_iter = 3 * n;
   bool check_first = false;
   // the two columns of this lane (n <= 64); out-of-range ones are clamped and never win
@@ -400,6 +402,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
         continue;
       }
       k += 1;
+      nappend += 1;
       mask |= 1ull << bj;
     }
     check_first = false;
@@ -468,6 +471,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
   double acc = 0.0;
   _Pragma("unroll 1") for (int j = lane; j < n; j += 32) acc = fma(V[GV_X + j], V[GV_X + j], acc);
   o.xnorm_sq = warp_sum(acc);
+  o.iters = iter, o.nappend = nappend;
   GP_ADD(13, k);
   GP_ADD(14, iter);
   GP_END(3);
