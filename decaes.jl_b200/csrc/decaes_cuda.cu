@@ -556,8 +556,10 @@ struct DeviceWs {
   cudaDeviceProp prop;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_pending = false;
+  int chunks_pending = 0;  // pipeline launches since the last collect_device_stats (one counter block each)
   int sm_count = 0;
 };
+#define DECAES_MAX_CHUNKS 8  // sub-slabs of one device's slab whose copies overlap the neighbours' kernels
 static std::mutex g_ws_mutex;
 static DeviceWs g_ws[64];
 
@@ -695,7 +697,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if ((rc = ensure(&ws.scratch, &ws.scratch_cap, (size_t)plan->grid * wpc * sl.total))) return rc;
   if ((rc = ensure(&ws.gram_set, &ws.gram_cap, (size_t)nA * P.a_elems))) return rc;
   P.gram_set = ws.gram_set;
-  if (!ws.counters) CUDA_TRY(cudaMalloc(&ws.counters, 32 * sizeof(unsigned long long)));
+  if (!ws.counters) CUDA_TRY(cudaMalloc(&ws.counters, DECAES_MAX_CHUNKS * 32 * sizeof(unsigned long long)));
   for (int i = 0; i < 4; i++)
     if (!ws.ev[i]) CUDA_TRY(cudaEventCreate(&ws.ev[i]));
   P.basis_rm = ws.basis_rm, P.basis_cm = ws.basis_cm, P.dbasis_cm = ws.dbasis_cm;
@@ -719,26 +721,31 @@ static int check_out(const decaes_t2map_out *out, const decaes_t2part_opts *part
 
 // enqueue setup + pipeline kernels on `stream` for device-resident data
 static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t nvox, int64_t stride,
-                           const decaes_t2map_out *o, cudaStream_t stream) {
+                           const decaes_t2map_out *o, cudaStream_t stream, int chunk = 0) {
   PipeParams &P = plan.P;
+  if (chunk < 0 || chunk >= DECAES_MAX_CHUNKS) return fail(DECAES_EINVAL, "bad chunk index");
   P.image = d_image, P.nvox = nvox, P.stride = stride;
   P.gdn = o->gdn, P.ggm = o->ggm, P.gva = o->gva, P.fnr = o->fnr, P.snr = o->snr, P.alpha = o->alpha, P.dist = o->dist;
   P.resnorm = o->resnorm, P.decaycurve = o->decaycurve, P.mu = o->mu, P.chi2factor = o->chi2factor;
   P.decaybasis = o->decaybasis;
   P.sfr = o->sfr, P.sgm = o->sgm, P.mfr = o->mfr, P.mgm = o->mgm;
   DeviceWs &ws = g_ws[dev];
-  CUDA_TRY(cudaMemsetAsync(ws.counters, 0, 32 * sizeof(unsigned long long), stream));
-  CUDA_TRY(cudaEventRecord(ws.ev[0], stream));
-  int nt = plan.S.nA * plan.S.nT2;
-  basis_setup_kernel<<<(nt + 63) / 64, 64, 0, stream>>>(plan.S);
-  CUDA_TRY(cudaGetLastError());
-  if (P.gram) {
-    long long ng = (long long)plan.S.nA * plan.S.nT2 * plan.S.nT2;
-    CUDA_TRY(cudaMemsetAsync(ws.gram_set, 0, sizeof(double) * (size_t)plan.S.nA * P.a_elems, stream));
-    gram_setup_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, stream>>>(plan.S, ws.gram_set, P.ldg, P.a_elems);
+  P.counters = ws.counters + 32 * chunk;
+  CUDA_TRY(cudaMemsetAsync(P.counters, 0, 32 * sizeof(unsigned long long), stream));
+  if (chunk == 0) {  // the per-run tables are shared by every chunk of the slab
+    CUDA_TRY(cudaEventRecord(ws.ev[0], stream));
+    int nt = plan.S.nA * plan.S.nT2;
+    basis_setup_kernel<<<(nt + 63) / 64, 64, 0, stream>>>(plan.S);
     CUDA_TRY(cudaGetLastError());
+    if (P.gram) {
+      long long ng = (long long)plan.S.nA * plan.S.nT2 * plan.S.nT2;
+      CUDA_TRY(cudaMemsetAsync(ws.gram_set, 0, sizeof(double) * (size_t)plan.S.nA * P.a_elems, stream));
+      gram_setup_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, stream>>>(plan.S, ws.gram_set, P.ldg, P.a_elems);
+      CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(ws.ev[1], stream));
+    ws.chunks_pending = 0;
   }
-  CUDA_TRY(cudaEventRecord(ws.ev[1], stream));
   int64_t ngroups = (nvox + DECAES_GROUP - 1) / DECAES_GROUP;
   int grid = (int)std::min<int64_t>(plan.grid, std::max<int64_t>((ngroups + plan.warps_per_cta - 1) / plan.warps_per_cta, 1));
   CUDA_TRY(cudaMemcpyToSymbolAsync(cP, &P, sizeof(PipeParams), 0, cudaMemcpyHostToDevice, stream));
@@ -768,8 +775,9 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
     memset(&attr, 0, sizeof attr);
     cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);  // later work on this stream: default policy
   }
-  CUDA_TRY(cudaEventRecord(ws.ev[2], stream));
+  CUDA_TRY(cudaEventRecord(ws.ev[2], stream));  // re-recorded by every chunk: ev[1] -> ev[2] spans all of them
   ws.ev_pending = true;
+  ws.chunks_pending = chunk + 1;
   return DECAES_OK;
 }
 
@@ -780,8 +788,11 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
   float a = 0, b = 0;
   CUDA_TRY(cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]));
   CUDA_TRY(cudaEventElapsedTime(&b, ws.ev[1], ws.ev[2]));
-  unsigned long long c[32];
-  CUDA_TRY(cudaMemcpy(c, ws.counters, sizeof c, cudaMemcpyDeviceToHost));
+  unsigned long long c[32] = {0}, call[DECAES_MAX_CHUNKS * 32];
+  const int nch = std::max(1, std::min(ws.chunks_pending, DECAES_MAX_CHUNKS));
+  CUDA_TRY(cudaMemcpy(call, ws.counters, (size_t)nch * 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < nch; k++)
+    for (int i = 0; i < 32; i++) c[i] += call[32 * k + i];
   st->setup_ms = std::max(st->setup_ms, (double)a);
   st->pipeline_ms = std::max(st->pipeline_ms, (double)b);
   st->voxels_processed += (int64_t)c[1];
@@ -823,8 +834,9 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
     cudaMemcpyToSymbol(g_khist, z, sizeof kh);
   }
 #endif
-  st->kernel_launches += 3;
+  st->kernel_launches += 2 + nch;
   ws.ev_pending = false;
+  ws.chunks_pending = 0;
   return DECAES_OK;
 }
 
@@ -1005,32 +1017,60 @@ static int run_slab(SlabJob &job, const double *image, int64_t Nvox, const decae
   }
   double *dbuf = nullptr;
   CUDA_TRY(cudaMalloc(&dbuf, total * sizeof(double)));
-  cudaEvent_t e0, e1, e2, e3;
-  cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventCreate(&e2), cudaEventCreate(&e3);
-  CUDA_TRY(cudaEventRecord(e0, st));
-  CUDA_TRY(cudaMemcpy2DAsync(dbuf, nv * sizeof(double), image + job.v0, Nvox * sizeof(double), nv * sizeof(double), nTE,
-                             cudaMemcpyHostToDevice, st));
   decaes_t2map_out dout;
   double **dptr = (double **)&dout;
   for (int f = 0; f < 16; f++) dptr[f] = hostp[f] ? dbuf + off[f] : nullptr;
-  if (opts->alpha_provided)
-    CUDA_TRY(cudaMemcpyAsync(dout.alpha, out->alpha + job.v0, nv * sizeof(double), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaEventRecord(e1, st));
-  rc = launch_pipeline(plan, job.dev, dbuf, nv, nv, &dout, st);
-  if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(e2, st));
-  for (int f = 0; f < 16; f++)
-    if (hostp[f])
-      CUDA_TRY(cudaMemcpy2DAsync(hostp[f] + job.v0, Nvox * sizeof(double), dptr[f], nv * sizeof(double), nv * sizeof(double),
-                                 mult[f], cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaEventRecord(e3, st));
+  // The slab is processed as up to DECAES_MAX_CHUNKS sub-slabs: all host-to-device copies are queued up front on
+  // a copy stream, the kernels run back to back on the compute stream as their inputs land, and every sub-slab's
+  // results go back while the next one computes.  Exposed transfer time = first copy in + last copy out.
+  int nchunks = (int)std::min<int64_t>(4, std::max<int64_t>(1, nv / 65536));
+  if (const char *e = getenv("DECAES_CHUNKS")) nchunks = std::max(1, std::min(DECAES_MAX_CHUNKS, atoi(e)));
+  nchunks = (int)std::min<int64_t>(nchunks, nv);
+  cudaStream_t sc;
+  CUDA_TRY(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1, e2, e3, evin[DECAES_MAX_CHUNKS], evdone[DECAES_MAX_CHUNKS];
+  cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventCreate(&e2), cudaEventCreate(&e3);
+  for (int c = 0; c < nchunks; c++)
+    cudaEventCreateWithFlags(&evin[c], cudaEventDisableTiming), cudaEventCreateWithFlags(&evdone[c], cudaEventDisableTiming);
+  auto bound = [&](int c) { return ((nv * c / nchunks) / DECAES_GROUP) * DECAES_GROUP; };
+  CUDA_TRY(cudaEventRecord(e0, sc));
+  for (int c = 0; c < nchunks; c++) {
+    const int64_t a = bound(c), b = (c + 1 == nchunks) ? nv : bound(c + 1);
+    CUDA_TRY(cudaMemcpy2DAsync(dbuf + a, nv * sizeof(double), image + job.v0 + a, Nvox * sizeof(double), (b - a) * sizeof(double),
+                               nTE, cudaMemcpyHostToDevice, sc));
+    if (opts->alpha_provided)
+      CUDA_TRY(cudaMemcpyAsync(dout.alpha + a, out->alpha + job.v0 + a, (b - a) * sizeof(double), cudaMemcpyHostToDevice, sc));
+    CUDA_TRY(cudaEventRecord(evin[c], sc));
+    if (c == 0) CUDA_TRY(cudaEventRecord(e1, sc));
+  }
+  for (int c = 0; c < nchunks; c++) {
+    const int64_t a = bound(c), b = (c + 1 == nchunks) ? nv : bound(c + 1);
+    decaes_t2map_out dc = dout;
+    double **dcp = (double **)&dc;
+    for (int f = 0; f < 16; f++)
+      if (dcp[f]) dcp[f] += a;
+    CUDA_TRY(cudaStreamWaitEvent(st, evin[c], 0));
+    rc = launch_pipeline(plan, job.dev, dbuf + a, b - a, nv, &dc, st, c);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(evdone[c], st));
+    CUDA_TRY(cudaStreamWaitEvent(sc, evdone[c], 0));
+    if (c + 1 == nchunks) CUDA_TRY(cudaEventRecord(e2, sc));
+    for (int f = 0; f < 16; f++)
+      if (hostp[f])
+        CUDA_TRY(cudaMemcpy2DAsync(hostp[f] + job.v0 + a, Nvox * sizeof(double), dptr[f] + a, nv * sizeof(double),
+                                   (b - a) * sizeof(double), mult[f], cudaMemcpyDeviceToHost, sc));
+  }
+  CUDA_TRY(cudaEventRecord(e3, sc));
+  CUDA_TRY(cudaStreamSynchronize(sc));
   CUDA_TRY(cudaStreamSynchronize(st));
   float h2d = 0, d2h = 0;
   cudaEventElapsedTime(&h2d, e0, e1), cudaEventElapsedTime(&d2h, e2, e3);
-  job.st.h2d_ms = h2d, job.st.d2h_ms = d2h;
+  job.st.h2d_ms = h2d, job.st.d2h_ms = d2h;  // exposed parts: first sub-slab in, last sub-slab out
   rc = collect_device_stats(job.dev, &job.st);
   cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2), cudaEventDestroy(e3);
+  for (int c = 0; c < nchunks; c++) cudaEventDestroy(evin[c]), cudaEventDestroy(evdone[c]);
   cudaFree(dbuf);
+  cudaStreamDestroy(sc);
   cudaStreamDestroy(st);
   return rc;
 }
