@@ -195,8 +195,9 @@ __global__ void gram_setup_kernel(const __grid_constant__ SetupParams S, double 
 // Persistent CTAs of P.warps_per_cta warps, one CTA per SM.  Every warp owns a slice of the dynamic
 // shared memory and processes its own voxels; CTA barriers keep the warps in the same PHASE of the
 // per-voxel chain (flip-angle fit | EPG basis | regularised solve + outputs).  The kernel is
-// instruction-cache bound (ncu: stall_no_inst dominates when warps wander through ~170 KB of hot
-// code independently), and warps that execute the same phase share its cache lines.
+// instruction-fetch bound (ncu: stall_no_inst dominates when warps wander through the ~100 KB of hot
+// code independently; every phase runs 10-20 % slower when phases overlap), and warps that execute
+// the same phase share its cache lines.
 template <bool GRAM>
 __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kernel(const __grid_constant__ PipeParams P) {
   extern __shared__ __align__(128) double smem[];
