@@ -592,7 +592,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.ld = nT2 | 1;
   P.copy_elems = (nTE * P.ld + 1) & ~1;
   P.rows_alloc = (o->reg == DECAES_REG_NONE) ? nTE : nTE + nT2;
-  P.epg_kmax = nTE / 2 + 3;
+  P.epg_kmax = nTE - nTE / 2 + 1;  // phase states 1..K touched by the truncated recursion (stored at 0..K-1)
   int epg_elems = 3 * P.epg_kmax * 32;
   P.a_elems = std::max(std::max(P.rows_alloc * P.ld, P.copy_elems), epg_elems);
   // solver variant: normal-equation active set (default) or the QR port (DECAES_SOLVER=qr, kept for A/B checks)
@@ -638,7 +638,23 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     memcpy(P.weights, pt.weights, sizeof pt.weights);
   }
 
-  SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems, P.gram);
+  // Shared memory per warp decides how many voxels an SM holds.  Moving the two coldest per-voxel tables (cached
+  // solutions, L-curve state records) to the warp's global scratch costs ~1 % each and is done when it buys a warp.
+  P.spill = 0;
+  if (P.gram) {
+    int optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int best_w = 0;
+    bool best_epg = false;
+    for (int sp : {0, 1, 3}) {
+      SmemLayout Ls(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, sp);
+      int w = (int)std::min<size_t>(DECAES_MAX_WARPS, ((size_t)optin - 1024) / Ls.total_bytes);
+      const bool epg_ok = 3 * P.epg_kmax * 32 <= Ls.bd;  // the shared-memory EPG must still fit in front of the signal
+      if ((epg_ok && !best_epg && w >= 1) || (epg_ok == best_epg && w > best_w)) best_w = w, best_epg = epg_ok, P.spill = sp;
+    }
+    if (const char *e = getenv("DECAES_SPILL")) P.spill = atoi(e) & 3;
+  }
+  SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, P.spill);
   plan->smem_bytes = L.total_bytes;
   // the solver block + search caches (everything in front of the voxel's signal) are idle while the basis is built
   P.epg_smem = P.gram && 3 * P.epg_kmax * 32 <= L.bd;

@@ -38,6 +38,7 @@ struct PipeParams {
   int gram, ldg;            // solver variant (1 = normal-equation active set), leading dimension of G
   int warps_per_cta, smem_per_warp;  // CTA shape: bytes of dynamic shared memory owned by each warp
   int fa_warm;              // warm-start flip-angle probes from a probed angle at most this many grid steps away (0 = never)
+  int spill;                // which per-voxel tables live in global scratch instead of shared memory (SmemLayout)
   int sync_groups;          // 1: CTA-wide phase barriers; g > 1: one barrier per group of warps (warp id mod g)
   int sync_mask;            // which intra-round CTA barriers are active (bit 0: after flip angle, bit 1: after basis)
   int epg_smem;             // EPG at the fitted angle keeps its states in shared memory (lane <-> component)
@@ -74,7 +75,9 @@ struct ScratchLayout {
 struct SmemLayout {
   int A, b, u, x, w, bd, sig, fit, slot_mu, slot_r2, slot_x2, slot_mask, idx, bar, total_bytes;
   int M, c, y, s, t1, t2, lc_pts, lc_states, slots_x, fa_u, fa_du, fa_mask;  // Gram solver only
-  __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems, int gram) {
+  // spill (Gram solver): bit 0 = the cached solutions (slots_x), bit 1 = the L-curve state records live in the warp's
+  // global scratch instead (one L2 round trip per solve / per L-curve step, 2.5 KB each of shared memory back)
+  __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems, int gram, int spill = 0) {
     int o = 0;
     b = u = M = c = y = s = t1 = t2 = lc_pts = lc_states = slots_x = fa_u = fa_du = fa_mask = 0;
     if (gram) {
@@ -82,8 +85,8 @@ struct SmemLayout {
       c = GV_C, y = GV_Y, s = GV_S, t1 = GV_T1, t2 = GV_T2, x = GV_X, w = GV_W, idx = GV_P;
       A = GV_T, o = GV_T + a_elems;
       lc_pts = o, o += 4 * DECAES_LC_MAX;
-      lc_states = o, o += 5 * DECAES_LC_MAX;
-      slots_x = o, o += DECAES_NCACHE * nT2;
+      if (!(spill & 2)) lc_states = o, o += 5 * DECAES_LC_MAX;
+      if (!(spill & 1)) slots_x = o, o += DECAES_NCACHE * nT2;
       // the flip-angle tables are dead once the angle is fitted: they alias the L-curve caches
       fa_u = lc_pts, fa_du = lc_pts + DECAES_MAX_ANGLES, fa_mask = lc_pts + 2 * DECAES_MAX_ANGLES;
       static_assert(3 * DECAES_MAX_ANGLES <= 9 * DECAES_LC_MAX, "flip-angle tables must fit in the L-curve caches");
@@ -94,13 +97,15 @@ struct SmemLayout {
       x = o, o += nT2;
       w = o, o += nT2;
     }
-    bd = o, o += nTE;
-    sig = 0;
+    // everything in front of `bd` is dead while the EPG basis is built (the EPG keeps its phase states there);
+    // the voxel's signal and the mbarrier must survive it
     fit = o, o += nTE;
     slot_mu = o, o += DECAES_NCACHE;
     slot_r2 = o, o += DECAES_NCACHE;
     slot_x2 = o, o += DECAES_NCACHE;
     slot_mask = o, o += DECAES_NCACHE;
+    bd = o, o += nTE;
+    sig = 0;
     bar = o, o += 2;
     if (!gram) idx = o, o += (nT2 + 1) / 2;
     total_bytes = ((o * 8) + 15) & ~15;
@@ -170,7 +175,7 @@ struct Warp {
 
   __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
       : sl(p.nTE, p.nT2, p.copy_elems, p.reg == 2) {
-    SmemLayout L(p.nTE, p.nT2, p.rows_alloc, p.a_elems, p.gram);
+    SmemLayout L(p.nTE, p.nT2, p.rows_alloc, p.a_elems, p.gram, p.spill);
     ws.A = smem + L.A, ws.b = smem + L.b, ws.u = smem + L.u, ws.x = smem + L.x, ws.w = smem + L.w;
     ws.idx = (int *)(smem + L.idx);
     ws.ld = p.ld, ws.n = p.nT2, ws.m0 = p.nTE;
@@ -179,7 +184,9 @@ struct Warp {
     gws.t1 = smem + L.t1, gws.t2 = smem + L.t2, gws.P = (int *)(smem + L.idx);
     slot_mask = (unsigned long long *)(smem + L.slot_mask);
     if (p.gram) {
-      lc_pts_p = smem + L.lc_pts, lc_states_p = smem + L.lc_states, slots_x_p = smem + L.slots_x;
+      lc_pts_p = smem + L.lc_pts;
+      lc_states_p = (p.spill & 2) ? gscratch + sl.lc_states : smem + L.lc_states;
+      slots_x_p = (p.spill & 1) ? gscratch + sl.slots_x : smem + L.slots_x;
       fa_u_p = smem + L.fa_u, fa_du_p = smem + L.fa_du, fa_mask_p = (unsigned long long *)(smem + L.fa_mask);
     } else {
       lc_pts_p = gscratch + sl.lc_pts, lc_states_p = gscratch + sl.lc_states, slots_x_p = gscratch + sl.slots_x;
@@ -398,7 +405,7 @@ struct Warp {
     const double E1 = cP.E1;
     // the three state arrays never alias: lets the compiler overlap the loads of one state with the stores of the previous one
     double *const sF = S + lane, *const sB = S + K * 32 + lane, *const sZ = S + 2 * K * 32 + lane;
-#define ST(c, k) ((c) == 0 ? sF : (c) == 1 ? sB : sZ)[(k) * 32]
+#define ST(c, k) ((c) == 0 ? sF : (c) == 1 ? sB : sZ)[((k)-1) * 32]
     for (int j0 = 0; j0 < n; j0 += 32) {
       const int j = j0 + lane;
       const bool act = j < n;
@@ -487,7 +494,7 @@ struct Warp {
     const double s2h = __dmul_rn(sh, sh), c2h = __dmul_rn(ch, ch), sin1 = __dmul_rn(__dmul_rn(2.0, sh), ch);
     const double c2hi = (1 + cosi) / 2, s2hi = 1 - c2hi;
     const double E1 = cP.E1, m0 = sh;
-#define ST(c, k) S[((c)*K + (k)) * 32 + lane]
+#define ST(c, k) S[((c)*K + (k)-1) * 32 + lane]
 #define DOT3(u0, u1, u2) __dadd_rn(__dadd_rn(__dmul_rn(u0, mF), __dmul_rn(u1, mFb)), __dmul_rn(u2, mZ))
     _Pragma("unroll 1") for (int j0 = 0; j0 < n; j0 += 32) {
       const int j = j0 + lane;
@@ -718,7 +725,7 @@ struct Warp {
   // does not exceed the current state's.  Returns its index or -1.
   __device__ __noinline__ int lc_backtrack(double xb, double wcur, int nst) {
     const int lane = this->lane;
-    VIEWG(double, lc_states_p);
+    double *const lc_states_p = this->lc_states_p;  // shared or global (PipeParams::spill)
     const double *sts = lc_states_p;
     unsigned long long key = ~0ull;  // widths are >= 0: their bit patterns order like the values
     int bk = -1;
@@ -739,7 +746,7 @@ struct Warp {
   __device__ __noinline__ double lcurve_corner(const double *Asrc) {
     const int lane = this->lane;
     VIEWG(double, lc_pts_p);
-    VIEWG(double, lc_states_p);
+    double *const lc_states_p = this->lc_states_p;  // shared or global (PipeParams::spill)
     const double phi = 1.618033988749895, xtol = 1e-4, Ptol = 1e-4, Ctol = 1e-4;
     double *pts = lc_pts_p, *sts = lc_states_p;
     int npts = 0, nst = 0;
@@ -1060,7 +1067,7 @@ struct Warp {
     const int nTE = cP.nTE;
     // lane <-> echoes lane, lane + 32 (, lane + 64): all of them advance together so that one L2 round
     // trip serves up to 12 loads per lane (A lives in L2; the loop is latency bound)
-    const int i0 = lane, i1 = lane + 32 < nTE ? lane + 32 : lane, i2 = lane + 64 < nTE ? lane + 64 : lane;
+    const int i0 = lane < nTE ? lane : 0, i1 = lane + 32 < nTE ? lane + 32 : i0, i2 = lane + 64 < nTE ? lane + 64 : i0;
     double r0 = bd[i0], r1 = bd[i1], r2 = bd[i2];
     _Pragma("unroll 4") for (int t = 0; t < k; t++) {
       const double *col = Acm + gws.P[t] * nTE;
@@ -1342,7 +1349,7 @@ struct Warp {
     VIEW(double, slot_r2);
     VIEW(double, slot_x2);
     VIEW(unsigned long long, slot_mask);
-    VIEW(double, slots_x_p);
+    double *const slots_x_p = this->slots_x_p;  // shared or global (PipeParams::spill)
     VIEW(double, V);
     VIEW_GWS();
     const int n = cP.nT2;
@@ -1449,7 +1456,7 @@ struct Warp {
     const int lane = this->lane;
     VIEW(double, bd);
     VIEW(double, fit);
-    VIEWG(double, slots_x_p);
+    double *const slots_x_p = this->slots_x_p;  // shared or global (PipeParams::spill)
     VIEWG(double, lc_pts_p);
     const NnlsWs ws = this->ws;
     SH(ws.x);
