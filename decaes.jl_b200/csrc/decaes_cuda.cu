@@ -593,11 +593,15 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.copy_elems = (nTE * P.ld + 1) & ~1;
   P.rows_alloc = (o->reg == DECAES_REG_NONE) ? nTE : nTE + nT2;
   P.epg_kmax = nTE - nTE / 2 + 1;  // phase states 1..K touched by the truncated recursion (stored at 0..K-1)
-  int epg_elems = 3 * P.epg_kmax * 32;
-  P.a_elems = std::max(std::max(P.rows_alloc * P.ld, P.copy_elems), epg_elems);
   // solver variant: normal-equation active set (default) or the QR port (DECAES_SOLVER=qr, kept for A/B checks)
   const char *sv = getenv("DECAES_SOLVER");
   P.gram = !(sv && strcmp(sv, "qr") == 0);
+  {
+    const int npass = (nT2 + 31) / 32;
+    P.epg_lanes = P.gram ? (nT2 + npass - 1) / npass : 32;  // the QR port keeps 32 lanes per pass
+  }
+  int epg_elems = 3 * P.epg_kmax * 32;
+  P.a_elems = std::max(std::max(P.rows_alloc * P.ld, P.copy_elems), epg_elems);
   // Brent-based choosers (gcv / chi2 / mdp) are numerically stable searches: keep their inputs at
   // reference-level accuracy.  The L-curve search flips on 1-ulp noise anyway (tests/test_oracle_sensitivity.py).
   P.refine_tikh = (o->reg != DECAES_REG_LCURVE);
@@ -649,7 +653,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     for (int sp : {0, 1, 3}) {
       SmemLayout Ls(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, sp);
       int w = (int)std::min<size_t>(DECAES_MAX_WARPS, ((size_t)optin - 1024) / Ls.total_bytes);
-      const bool epg_ok = 3 * P.epg_kmax * 32 <= Ls.bd;  // the shared-memory EPG must still fit in front of the signal
+      const bool epg_ok = 3 * P.epg_kmax * (P.epg_lanes + 1) <= Ls.bd;  // the shared-memory EPG must still fit in front of the signal
       if ((epg_ok && !best_epg && w >= 1) || (epg_ok == best_epg && w > best_w)) best_w = w, best_epg = epg_ok, P.spill = sp;
     }
     if (const char *e = getenv("DECAES_SPILL")) P.spill = atoi(e) & 3;
@@ -657,11 +661,11 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, P.spill);
   plan->smem_bytes = L.total_bytes;
   // the solver block + search caches (everything in front of the voxel's signal) are idle while the basis is built
-  P.epg_smem = P.gram && 3 * P.epg_kmax * 32 <= L.bd;
+  P.epg_smem = P.gram && 3 * P.epg_kmax * (P.epg_lanes + 1) <= L.bd;
   if (const char *e = getenv("DECAES_EPG_SMEM")) P.epg_smem = P.epg_smem && atoi(e);
   P.refcon = o->RefConAngle;
-  if (P.refcon != 180.0 && !fixed && !(P.gram && 3 * P.epg_kmax * 32 <= L.bd))
-    return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 needs the Gram solver and %d bytes of shared EPG scratch per warp", 3 * P.epg_kmax * 32 * 8);
+  if (P.refcon != 180.0 && !fixed && !(P.gram && 3 * P.epg_kmax * (P.epg_lanes + 1) <= L.bd))
+    return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 needs the Gram solver and %d bytes of shared EPG scratch per warp", 3 * P.epg_kmax * (P.epg_lanes + 1) * 8);
   if (P.refcon != 180.0) P.epg_smem = 1;
   {
     std::lock_guard<std::mutex> lk(g_ws_mutex);

@@ -20,7 +20,8 @@ struct PipeParams {
   int nseed, maxeval;
   int fixed_alpha;      // SetFlipAngle given
   int alpha_provided;   // B1 map in out.alpha
-  int epg_kmax;         // highest phase state index + 2
+  int epg_kmax;         // phase states kept by the shared-memory EPG
+  int epg_lanes;        // components per pass of the shared-memory EPG (n split evenly over ceil(n/32) passes)
   int has_part, sp_lo, sp_hi, mp_lo, mp_hi, has_sigmoid;
   int8_t seeds[DECAES_MAX_ANGLES];
   double TE, T1, Threshold, Chi2Factor, NoiseLevel, SetFlipAngle, E1, refcon;
@@ -404,11 +405,15 @@ struct Warp {
     const double m0 = sind_0_180(alpha_deg / 2);
     const double E1 = cP.E1;
     // the three state arrays never alias: lets the compiler overlap the loads of one state with the stores of the previous one
-    double *const sF = S + lane, *const sB = S + K * 32 + lane, *const sZ = S + 2 * K * 32 + lane;
-#define ST(c, k) ((c) == 0 ? sF : (c) == 1 ? sB : sZ)[((k)-1) * 32]
-    for (int j0 = 0; j0 < n; j0 += 32) {
-      const int j = j0 + lane;
-      const bool act = j < n;
+    // LW lanes per pass: the n components are split evenly over ceil(n/32) passes (40 -> 2 x 20), which costs the same
+    // as 32 + 8 and shrinks the scratch to 3 K LW doubles
+    const int LW = cP.epg_lanes, LS = LW + 1;  // row stride: one spare column that all idle lanes share
+    const int ls = lane < LW ? lane : LW;
+    double *const sF = S + ls, *const sB = S + K * LS + ls, *const sZ = S + 2 * K * LS + ls;
+#define ST(c, k) ((c) == 0 ? sF : (c) == 1 ? sB : sZ)[((k)-1) * LS]
+    for (int j0 = 0; j0 < n; j0 += LW) {
+      const int j = j0 + ls;
+      const bool act = lane < LW && j < n;
       const double E2 = act ? cP.E2[j] : 0.0;
       const double E2h = __dmul_rn(E2, E2) / 2, E1E2 = __dmul_rn(E1, E2), E1sq = __dmul_rn(E1, E1);
       const double a = E2h, b = __dmul_rn(E2h, cosa), c = __dmul_rn(E1E2, sina), d = __dmul_rn(E1sq, cosa);
@@ -494,11 +499,13 @@ struct Warp {
     const double s2h = __dmul_rn(sh, sh), c2h = __dmul_rn(ch, ch), sin1 = __dmul_rn(__dmul_rn(2.0, sh), ch);
     const double c2hi = (1 + cosi) / 2, s2hi = 1 - c2hi;
     const double E1 = cP.E1, m0 = sh;
-#define ST(c, k) S[((c)*K + (k)-1) * 32 + lane]
+    const int LW = cP.epg_lanes, LS = LW + 1;  // row stride: one spare column that all idle lanes share
+    const int ls = lane < LW ? lane : LW;
+#define ST(c, k) S[((c)*K + (k)-1) * LS + ls]
 #define DOT3(u0, u1, u2) __dadd_rn(__dadd_rn(__dmul_rn(u0, mF), __dmul_rn(u1, mFb)), __dmul_rn(u2, mZ))
-    _Pragma("unroll 1") for (int j0 = 0; j0 < n; j0 += 32) {
-      const int j = j0 + lane;
-      const bool act = j < n;
+    _Pragma("unroll 1") for (int j0 = 0; j0 < n; j0 += LW) {
+      const int j = j0 + ls;
+      const bool act = lane < LW && j < n;
       const double E2 = act ? cP.E2[j] : 0.0;
       const double E2sq = __dmul_rn(E2, E2), E1E2 = __dmul_rn(E1, E2);
       const double a1 = __dmul_rn(E2sq, c2h), b1 = __dmul_rn(E2sq, s2h), c1 = __dmul_rn(E1E2, sin1);
