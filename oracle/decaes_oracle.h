@@ -143,6 +143,32 @@ typedef void (*orc_fg_fn)(int I /* 1-based grid index */, double *u, double *du,
 void orc_surrogate_search(orc_fg_fn fg, void *ctx, const double *grid, int ngrid, int mineval,
                           int maxeval, double *x_opt, double *u_opt, int *order, int *norder);
 
+/* same search with CubicSplineSurrogate(...; legacy = true)  splines.jl:456-500: suggest_point is the
+ * sampled minimum of the FITPACK interpolating spline through the probed points (du is ignored) */
+void orc_surrogate_search_legacy(orc_fg_fn fg, void *ctx, const double *grid, int ngrid, int mineval,
+                                 int maxeval, double *x_opt, double *u_opt, int *order, int *norder);
+
+/* ---------- legacy = true algorithms (oracle/orc_spline.c) ---------- */
+#define ORC_SPLINE_MAX 64
+/* FITPACK curfit(iopt=0, s=0) + splev as wrapped by Dierckx.Spline1D (src/splines.jl:311-314) */
+int orc_fitpack_interp(const double *x, const double *y, int m, int k, double *t /* m+k+1 */, double *c /* m */);
+void orc_fitpack_splev(const double *t, int n, const double *c, int k, const double *x, int m, double *y);
+/* Julia's start:step:stop for Float64 (base/twiceprecision.jl) */
+typedef struct {
+  int rational;
+  int64_t start_n, step_n, den, len;
+  double start, step;
+} orc_jl_range_t;
+void orc_jl_range(double start, double step, double stop, orc_jl_range_t *r);
+double orc_jl_range_at(const orc_jl_range_t *r, int64_t i /* 0-based */);
+/* src/splines.jl:419-446 */
+int orc_spline_opt_legacy(const double *X, const double *Y, int m, double *x, double *y);
+int orc_spline_root_legacy(const double *X, const double *Y, int m, double value, double *x);
+/* src/lsqnonneg.jl:595-636 with legacy = true; f(mu) -> res2(mu) */
+int orc_chi2_search_legacy(orc_fn1 f, void *ctx, double res2min, double chi2fact, double *mu, double *res2);
+/* lsqnonneg_chi2!(work, chi2_target, legacy = true)  src/lsqnonneg.jl:504-533; *early = 3 when mu_final == 0 */
+const double *orc_lsqnonneg_chi2_legacy(orc_reg_work *w, double chi2_target, double *mu, double *chi2, int *early);
+
 /* ---------- pipeline (src/T2mapSEcorr.jl, src/T2partSEcorr.jl) ---------- */
 typedef struct {
   int64_t voxels_processed;

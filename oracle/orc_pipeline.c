@@ -65,8 +65,8 @@ int orc_validate_t2map_opts(const decaes_t2map_opts *o, char *msg, int msglen) {
   if (!(0.0 <= o->RefConAngle && o->RefConAngle <= 180.0)) FAIL("Refocusing control angle must be in the range [0, 180]");
   if (!isnan(o->SetFlipAngle) && !(0.0 <= o->SetFlipAngle && o->SetFlipAngle <= 180.0))
     FAIL("Fixed flip angle must be in the range [0, 180]");
-  if (o->legacy) {
-    if (msg) snprintf(msg, msglen, "legacy = true is outside the accelerated path");
+  if (o->legacy && o->nRefAngles > ORC_SPLINE_MAX) {
+    if (msg) snprintf(msg, msglen, "legacy = true supports at most %d refocusing angles", ORC_SPLINE_MAX);
     return DECAES_EUNSUPPORTED;
   }
   return DECAES_OK;
@@ -365,8 +365,12 @@ int orc_t2map(const double *image, int64_t nvox, int64_t stride, const decaes_t2
         alpha = o->SetFlipAngle;
       } else { /* optimize_flip_angle!  :409-423 */
         double u_opt;
-        orc_surrogate_search(fa_loss_grad, &vb, angles, nA, o->nRefAnglesMin, o->nRefAngles, &alpha, &u_opt,
-                             NULL, NULL);
+        if (o->legacy) /* CubicSplineSurrogate(...; legacy = true)  :401-402 */
+          orc_surrogate_search_legacy(fa_loss_grad, &vb, angles, nA, o->nRefAnglesMin, o->nRefAngles, &alpha, &u_opt,
+                                      NULL, NULL);
+        else
+          orc_surrogate_search(fa_loss_grad, &vb, angles, nA, o->nRefAnglesMin, o->nRefAngles, &alpha, &u_opt,
+                               NULL, NULL);
         epg_basis_at(&vb, alpha);
       }
 
@@ -387,7 +391,8 @@ int orc_t2map(const double *image, int64_t nvox, int64_t stride, const decaes_t2
           x = orc_lsqnonneg_gcv(vb.reg, &mu, &chi2);
           break;
         case DECAES_REG_CHI2:
-          x = orc_lsqnonneg_chi2(vb.reg, o->Chi2Factor, &mu, &chi2, &early);
+          x = o->legacy ? orc_lsqnonneg_chi2_legacy(vb.reg, o->Chi2Factor, &mu, &chi2, &early) /* :445, :495 */
+                        : orc_lsqnonneg_chi2(vb.reg, o->Chi2Factor, &mu, &chi2, &early);
           break;
         case DECAES_REG_MDP: {
           double sigma = o->NoiseLevel / max_signal; /* :501-502 */

@@ -394,6 +394,46 @@ const double *orc_lsqnonneg_chi2(orc_reg_work *w, double chi2_target, double *mu
   return x_unreg;
 }
 
+/* lsqnonneg_chi2!(work, chi2_target, legacy = true)  :504-533: method = :legacy */
+typedef struct {
+  orc_reg_work *w;
+  double res2_min;
+} legacy_ctx;
+
+static double f_res2_mu(double mu, void *ctx) { /* the do-block :523-527 */
+  legacy_ctx *c = (legacy_ctx *)ctx;
+  if (mu == 0) return c->res2_min;
+  cache_solve(c->w, mu);
+  return tikh_resnorm_sq(cache_cur(c->w->cache));
+}
+
+const double *orc_lsqnonneg_chi2_legacy(orc_reg_work *w, double chi2_target, double *mu, double *chi2, int *early) {
+  solve_unreg(w);
+  const double *x_unreg = w->nnls->x;
+  double res2_min = w->nnls->rnorm * w->nnls->rnorm;
+  if (early) *early = 0;
+  if (res2_min == 0 || w->nnls->nsetp == 0) { /* :510-515, same stale-slot note as the :brent method */
+    if (early) *early = 1;
+    *mu = 0.0, *chi2 = 1.0;
+    return x_unreg;
+  }
+  reset_cache(w->cache);
+  legacy_ctx lc = {w, res2_min};
+  double mu_final, res2_final;
+  if (orc_chi2_search_legacy(f_res2_mu, &lc, res2_min, chi2_target, &mu_final, &res2_final)) {
+    /* the doubling did not reach the target (the reference would not return): report NaN */
+    if (early) *early = 4;
+    *mu = NAN, *chi2 = NAN;
+    return x_unreg;
+  }
+  *mu = mu_final, *chi2 = res2_final / res2_min;
+  if (mu_final == 0) { /* :528-529; save_results! would read the stale cache slot (:465): counted */
+    if (early) *early = 3;
+    return x_unreg;
+  }
+  return cache_solve(w, mu_final); /* :531 — a cache hit, f(mu_final) was the last solve */
+}
+
 /* =================== MDP  :700-747 =================== */
 const double *orc_lsqnonneg_mdp(orc_reg_work *w, double delta, double *mu, double *chi2, int *early) {
   solve_unreg(w);

@@ -53,6 +53,7 @@ typedef struct {
   int numeval;
   int *order;
   int norder;
+  int legacy; /* CubicSplineSurrogate(...; legacy = true) :456-500 */
 } search_t;
 
 typedef struct {
@@ -124,6 +125,12 @@ static void initialize_rec(search_t *s, box_t b, int depth, int mineval, int max
 
 /* suggest_point :544-566 */
 static void suggest_point(const search_t *s, double *xo, double *uo) {
+  if (s->legacy) { /* CubicSplineSurrogate suggest_point :492-500 -> spline_opt_legacy :419-430 */
+    double ps[ORC_SPLINE_MAX], us[ORC_SPLINE_MAX];
+    for (int i = 0; i < s->npts; i++) ps[i] = s->grid[s->idx[i] - 1], us[i] = s->u[s->idx[i] - 1];
+    if (orc_spline_opt_legacy(ps, us, s->npts, xo, uo)) *xo = NAN, *uo = NAN;
+    return;
+  }
   int I0 = s->idx[0];
   double plast = s->grid[I0 - 1], ulast = s->u[I0 - 1], dlast = s->du[I0 - 1];
   double p = plast, u = ulast;
@@ -151,11 +158,11 @@ static box_t minimal_bounding_box(const search_t *s, double x) {
   }
 }
 
-void orc_surrogate_search(orc_fg_fn fg, void *ctx, const double *grid, int ngrid, int mineval,
-                          int maxeval, double *x_opt, double *u_opt, int *order, int *norder) {
+static void search_impl(orc_fg_fn fg, void *ctx, const double *grid, int ngrid, int mineval, int maxeval,
+                        double *x_opt, double *u_opt, int *order, int *norder, int legacy) {
   search_t s;
   memset(&s, 0, sizeof(s));
-  s.fg = fg, s.ctx = ctx, s.grid = grid, s.n = ngrid, s.order = order;
+  s.fg = fg, s.ctx = ctx, s.grid = grid, s.n = ngrid, s.order = order, s.legacy = legacy;
   s.seen_s = (unsigned char *)calloc(ngrid, 1);
   s.seen = (unsigned char *)calloc(ngrid, 1);
   s.u = (double *)malloc(sizeof(double) * ngrid);
@@ -182,4 +189,14 @@ void orc_surrogate_search(orc_fg_fn fg, void *ctx, const double *grid, int ngrid
   *x_opt = x, *u_opt = u;
   if (norder) *norder = s.norder;
   free(s.seen_s), free(s.seen), free(s.u), free(s.du), free(s.idx);
+}
+
+void orc_surrogate_search(orc_fg_fn fg, void *ctx, const double *grid, int ngrid, int mineval,
+                          int maxeval, double *x_opt, double *u_opt, int *order, int *norder) {
+  search_impl(fg, ctx, grid, ngrid, mineval, maxeval, x_opt, u_opt, order, norder, 0);
+}
+
+void orc_surrogate_search_legacy(orc_fg_fn fg, void *ctx, const double *grid, int ngrid, int mineval,
+                                 int maxeval, double *x_opt, double *u_opt, int *order, int *norder) {
+  search_impl(fg, ctx, grid, ngrid, mineval, maxeval, x_opt, u_opt, order, norder, 1);
 }

@@ -68,6 +68,11 @@ class Stats(C.Structure):
                 ("seconds", C.c_double), ("threads", C.c_int)]
 
 
+class JlRange(C.Structure):
+    _fields_ = [("rational", C.c_int), ("start_n", C.c_int64), ("step_n", C.c_int64), ("den", C.c_int64),
+                ("len", C.c_int64), ("start", C.c_double), ("step", C.c_double)]
+
+
 LCURVE_FN = C.CFUNCTYPE(None, C.c_double, dp, C.c_void_p)
 FN1 = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 FG_FN = C.CFUNCTYPE(None, C.c_int, dp, dp, C.c_void_p)
@@ -114,6 +119,17 @@ def lib():
                                          dp, dp]
         L.orc_hermite_minimize.argtypes = [C.c_double] * 6 + [dp, dp]
         L.orc_surrogate_search.argtypes = [FG_FN, C.c_void_p, dp, C.c_int, C.c_int, C.c_int, dp, dp, ip, ip]
+        L.orc_surrogate_search_legacy.argtypes = L.orc_surrogate_search.argtypes
+        L.orc_fitpack_interp.argtypes = [dp, dp, C.c_int, C.c_int, dp, dp]
+        L.orc_fitpack_splev.argtypes = [dp, C.c_int, dp, C.c_int, dp, C.c_int, dp]
+        L.orc_jl_range.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(JlRange)]
+        L.orc_jl_range_at.restype = C.c_double
+        L.orc_jl_range_at.argtypes = [C.POINTER(JlRange), C.c_int64]
+        L.orc_spline_opt_legacy.argtypes = [dp, dp, C.c_int, dp, dp]
+        L.orc_spline_root_legacy.argtypes = [dp, dp, C.c_int, C.c_double, dp]
+        L.orc_chi2_search_legacy.argtypes = [FN1, C.c_void_p, C.c_double, C.c_double, dp, dp]
+        L.orc_lsqnonneg_chi2_legacy.restype = dp
+        L.orc_lsqnonneg_chi2_legacy.argtypes = [C.POINTER(RegWork), C.c_double, dp, dp, ip]
         L.orc_t2map.argtypes = [dp, C.c_int64, C.c_int64, C.POINTER(abi.T2mapOpts), C.POINTER(abi.T2partOpts),
                                 C.POINTER(abi.T2mapOut), C.c_int, C.POINTER(Stats)]
         L.orc_t2part.argtypes = [dp, C.c_int64, C.c_int64, C.POINTER(abi.T2partOpts), dp, dp, dp, dp]
@@ -328,7 +344,7 @@ def hermite_minimize(a, b, u0, u1, m0, m1):
     return x.value, u.value
 
 
-def surrogate_search(fg, grid, mineval, maxeval):
+def surrogate_search(fg, grid, mineval, maxeval, legacy=False):
     grid = f64(grid)
 
     def cb(I, u, du, _c):
@@ -337,9 +353,62 @@ def surrogate_search(fg, grid, mineval, maxeval):
     order = np.zeros(len(grid) + 4, dtype=np.int32)
     norder = C.c_int()
     x, u = C.c_double(), C.c_double()
-    lib().orc_surrogate_search(FG_FN(cb), None, _p(grid), len(grid), mineval, maxeval, C.byref(x), C.byref(u),
+    fn = lib().orc_surrogate_search_legacy if legacy else lib().orc_surrogate_search
+    fn(FG_FN(cb), None, _p(grid), len(grid), mineval, maxeval, C.byref(x), C.byref(u),
                                order.ctypes.data_as(ip), C.byref(norder))
     return x.value, u.value, order[:norder.value].tolist()
+
+
+# ----------------------------------------------------------------------------- legacy = true helpers
+def fitpack_interp(x, y, k):
+    x, y = f64(x), f64(y)
+    t, c = np.zeros(len(x) + k + 1), np.zeros(len(x))
+    rc = lib().orc_fitpack_interp(_p(x), _p(y), len(x), k, _p(t), _p(c))
+    if rc != 0:
+        raise ValueError("orc_fitpack_interp failed")
+    return t, c
+
+
+def fitpack_splev(t, c, k, x):
+    t, c, x = f64(t), f64(c), f64(x)
+    y = np.zeros(len(x))
+    lib().orc_fitpack_splev(_p(t), len(t), _p(c), k, _p(x), len(x), _p(y))
+    return y
+
+
+def jl_range(start, step, stop):
+    r = JlRange()
+    lib().orc_jl_range(start, step, stop, C.byref(r))
+    return r
+
+
+def jl_range_values(start, step, stop):
+    r = jl_range(start, step, stop)
+    return np.array([lib().orc_jl_range_at(C.byref(r), i) for i in range(r.len)])
+
+
+def spline_opt_legacy(X, Y):
+    X, Y = f64(X), f64(Y)
+    x, y = C.c_double(), C.c_double()
+    if lib().orc_spline_opt_legacy(_p(X), _p(Y), len(X), C.byref(x), C.byref(y)):
+        raise ValueError("orc_spline_opt_legacy failed")
+    return x.value, y.value
+
+
+def spline_root_legacy(X, Y, value=0.0):
+    X, Y = f64(X), f64(Y)
+    x = C.c_double()
+    if lib().orc_spline_root_legacy(_p(X), _p(Y), len(X), value, C.byref(x)):
+        raise ValueError("orc_spline_root_legacy failed")
+    return x.value
+
+
+def chi2_search_legacy(f, res2min, chi2fact):
+    mu, r2 = C.c_double(), C.c_double()
+    rc = lib().orc_chi2_search_legacy(FN1(lambda m, _c: f(m)), None, res2min, chi2fact, C.byref(mu), C.byref(r2))
+    if rc:
+        raise ValueError("doubling did not terminate")
+    return mu.value, r2.value
 
 
 # ----------------------------------------------------------------------------- options
