@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdecaes_cuda.so")
 SOURCES = ["decaes_cuda.cu"]
-HEADERS = ["common.cuh", "nnls.cuh", "gram.cuh", "voxel.cuh", os.path.join("..", "..", "include", "decaes_cuda.h")]
+HEADERS = ["common.cuh", "nnls.cuh", "gram.cuh", "legacy.cuh", "voxel.cuh", os.path.join("..", "..", "include", "decaes_cuda.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -5,7 +5,7 @@
     python -m decaes_cli @settings.txt            (one argument per line, like the reference's settings files)
 
 Same flags, same interdependencies and messages, same output files (<name>.t2dist.mat, <name>.t2maps.mat,
-<name>.t2parts.mat).  Differences: `--bet` (FSL brain extraction) and `--legacy` are refused, PAR/REC inputs
+<name>.t2parts.mat).  Differences: `--bet` (FSL brain extraction) is refused, PAR/REC inputs
 are not read, MAT files are written as v5 (fileio.py), and `--ngpus` selects how many devices share a volume.
 When both --T2map and --T2part are given the T2part maps come from the fused epilogue of the same kernel.
 """
@@ -36,7 +36,7 @@ def build_parser():
     p.add_argument("--T2part", action="store_true", help="analyse 4D T2 distributions to produce parameter maps")
     p.add_argument("--quiet", "-q", action="store_true", help="suppress printing to the terminal")
     p.add_argument("--dry", action="store_true", help="execute dry run of processing without saving any results")
-    p.add_argument("--legacy", action="store_const", const=True, default=None, help="(deprecated) legacy algorithms: not available on the GPU")
+    p.add_argument("--legacy", action="store_const", const=True, default=None, help="(deprecated) use legacy settings and algorithms from the original MATLAB pipeline")
     g = p.add_argument_group("T2map/T2part required parameters")
     g.add_argument("--MatrixSize", nargs=3, type=int, help="inferred from the input image")
     g.add_argument("--nTE", type=int, help="inferred from the input image")
@@ -70,8 +70,8 @@ def build_parser():
 def parse_cli(args):
     """parse_cli + handle_cli_deprecations! + verify_cli_args! + clean_cli_args!  (src/main.jl:424-484)."""
     opts = vars(build_parser().parse_args(args))
-    if opts.get("legacy") is not None:
-        raise SystemExit("The flag --legacy is deprecated upstream and its algorithms are not implemented on the GPU.")
+    if opts.get("legacy") is not None:  # warn_deprecated_future_removed(:legacy)  src/main.jl:441-443, 457
+        warnings.warn("The flag --legacy is deprecated and will be removed in future releases.")
     if opts.get("Chi2Factor") is not None:
         if opts["RegParams"]:
             raise SystemExit("The flag --RegParams and the deprecated flag --Chi2Factor were both passed; use --RegParams only.")

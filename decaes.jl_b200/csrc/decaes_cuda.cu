@@ -10,6 +10,7 @@
 //   mock_image_kernel    synthetic MSE volume (src/utils.jl:623-658)
 //   dfma_peak_kernel     measured FP64 FMA peak for the roofline denominator
 #include <algorithm>
+#include <numeric>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -198,13 +199,13 @@ __global__ void gram_setup_kernel(const __grid_constant__ SetupParams S, double 
 // instruction-fetch bound (ncu: stall_no_inst dominates when warps wander through the ~100 KB of hot
 // code independently; every phase runs 10-20 % slower when phases overlap), and warps that execute
 // the same phase share its cache lines.
-template <bool GRAM>
+template <bool GRAM, bool LEGACY = false>
 __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kernel(const __grid_constant__ PipeParams P) {
   extern __shared__ __align__(128) double smem[];
   const int wid = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + wid;
   double *gscratch = P.scratch + (size_t)gwarp * P.scratch_per_warp;
-  Warp<GRAM> W(P, smem + (size_t)wid * (P.smem_per_warp / 8), gscratch);
+  Warp<GRAM, LEGACY> W(P, smem + (size_t)wid * (P.smem_per_warp / 8), gscratch);
   const int lane = lane_id();
   if (lane == 0) {
     mbar_init(W.bar, 1);
@@ -434,7 +435,6 @@ static int validate_map(const decaes_t2map_opts *o) {
   if (!(0.0 <= o->RefConAngle && o->RefConAngle <= 180.0)) return fail(DECAES_EINVAL, "Refocusing control angle must be in the range [0, 180]");
   if (!std::isnan(o->SetFlipAngle) && !(0.0 <= o->SetFlipAngle && o->SetFlipAngle <= 180.0))
     return fail(DECAES_EINVAL, "Fixed flip angle must be in the range [0, 180]");
-  if (o->legacy) return fail(DECAES_EUNSUPPORTED, "legacy = true is outside the accelerated path");
   if (o->nT2 > DECAES_MAX_NT2) return fail(DECAES_EUNSUPPORTED, "nT2 > %d is not supported", DECAES_MAX_NT2);
   if (o->nRefAngles > DECAES_MAX_ANGLES) return fail(DECAES_EUNSUPPORTED, "nRefAngles > %d is not supported", DECAES_MAX_ANGLES);
   if (o->nTE > 72) return fail(DECAES_EUNSUPPORTED, "nTE > 72 is not supported");
@@ -462,6 +462,61 @@ static void linrange(double a, double b, int n, double *out) {
   for (int i = 0; i < n; i++)
     out[i] = (double)(((long double)a * (long double)(n - 1 - i) + (long double)b * (long double)i) / (long double)(n - 1));
   out[0] = a, out[n - 1] = b;
+}
+// start:step:stop for Float64 as Julia's Base builds it (base/twiceprecision.jl: `rat`, the lift to rationals,
+// `floatrange`): the legacy searches scan knots[1]:0.001:knots[end] (src/splines.jl:422, 438) and every sample must be
+// the double Julia would produce.  When start, step and stop are small rationals the elements are
+// (start_n + i*step_n)/den rounded once; otherwise start + i*step taken literally (also rounded once).
+static void julia_rat(double x, long long *num, long long *den) {
+  double y = x;
+  long long a = 1, d = 1, b = 0, c = 0;
+  const double m = 16777216.0;  // maxintfloat(Float32): Base narrows Float64 before the continued fraction
+  while (std::fabs(y) <= m) {
+    const long long f = (long long)std::trunc(y);
+    y -= (double)f;
+    const long long a2 = f * a + c, b2 = f * b + d;
+    c = a, a = a2, d = b, b = b2;
+    if (!(std::max(std::llabs(a), std::llabs(b)) <= (long long)m)) {
+      *num = c, *den = d;
+      return;
+    }
+    if ((double)a / (double)b == x) break;
+    y = 1.0 / y;
+  }
+  *num = a, *den = b;
+}
+static LegacyRange julia_colon(double start, double step, double stop) {
+  LegacyRange r;
+  memset(&r, 0, sizeof r);
+  r.start = start, r.step = step;
+  auto between = [](double lo, double x, double hi) { return (lo <= x && x <= hi) || (hi <= x && x <= lo); };
+  long long step_n, step_d, start_n, start_d, stop_n, stop_d;
+  julia_rat(step, &step_n, &step_d);
+  if (step_d != 0 && (double)step_n / (double)step_d == step) {
+    julia_rat(start, &start_n, &start_d);
+    julia_rat(stop, &stop_n, &stop_d);
+    if (start_d != 0 && stop_d != 0 && (double)start_n / (double)start_d == start && (double)stop_n / (double)stop_d == stop) {
+      const long long den = start_d / std::gcd(start_d, step_d) * step_d;
+      const double mi = 9007199254740992.0;
+      if (den != 0 && std::fabs(start * (double)den) <= mi && std::fabs(step * (double)den) <= mi && den % start_d == 0 &&
+          den % step_d == 0) {
+        start_n = std::llround(start * (double)den), step_n = std::llround(step * (double)den);
+        long long len = std::max(0ll, (den * stop_n - stop_d * start_n + step_n * stop_d) / (step_n * stop_d));
+        if (between(start, start + (double)(len - 1) * step, stop + step / 2) && !between(start, start + (double)len * step, stop)) {
+          r.rational = 1, r.start_n = start_n, r.step_n = step_n, r.den = den, r.len = len;
+          return r;
+        }
+      }
+    }
+  }
+  const double lf = (stop - start) / step;
+  long long len = lf < 0 ? 0 : (lf == 0 ? 1 : std::llrint(lf) + 1);
+  if (lf > 0) {
+    const double stop2 = start + (double)(len - 1) * step;
+    len -= (start < stop && stop < stop2) + (start > stop && stop > stop2);
+  }
+  r.len = len;
+  return r;
 }
 static void logrange(double a, double b, int n, double *out) {  // src/utils.jl:7
   linrange(std::log(a), std::log(b), n, out);
@@ -627,6 +682,17 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     P.angles[0] = o->SetFlipAngle;
   else
     linrange(o->MinRefAngle, 180.0, nA, P.angles);
+  if (o->legacy) {
+    // legacy = true: CubicSplineSurrogate with the sampled spline minimum for the flip angle, doubling search +
+    // sampled spline root for Reg = chi2 (csrc/legacy.cuh); everything else is shared with the modern path
+    if (!P.gram) return fail(DECAES_EUNSUPPORTED, "legacy = true needs the default solver (unset DECAES_SOLVER)");
+    P.legacy = 1;
+    if (!fixed) {
+      P.lg_range = julia_colon(P.angles[0], 0.001, P.angles[nA - 1]);
+      if (P.lg_range.len < 1 || P.lg_range.len > (1ll << 24))
+        return fail(DECAES_EUNSUPPORTED, "legacy flip-angle scan of %lld samples is not supported", P.lg_range.len);
+    }
+  }
   if (!fixed && !o->alpha_provided) {
     std::vector<int> seeds = seed_order(nA, o->nRefAnglesMin, o->nRefAngles);
     P.nseed = (int)seeds.size();
@@ -693,7 +759,9 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.warps_per_cta = wpc, P.smem_per_warp = plan->smem_bytes;
   plan->warps_per_cta = wpc;
   plan->cta_smem = wpc * plan->smem_bytes;
-  if (P.gram)
+  if (P.legacy)
+    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
+  else if (P.gram)
     CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
   else
     CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
@@ -786,7 +854,9 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
     window = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
     if (!window) cudaGetLastError();
   }
-  if (P.gram)
+  if (P.legacy)
+    voxel_pipeline_kernel<true, true><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
+  else if (P.gram)
     voxel_pipeline_kernel<true><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
   else
     voxel_pipeline_kernel<false><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);

@@ -8,12 +8,15 @@
 #pragma once
 #include "nnls.cuh"
 #include "gram.cuh"
+#include "legacy.cuh"
 
 namespace decaes {
 
 struct PipeParams {
   // sizes
   int nTE, nT2, ld, nA, reg;
+  int legacy;           // legacy = true (src/types.jl:20-21): sampled-spline flip-angle and chi2 searches (legacy.cuh)
+  LegacyRange lg_range; // angles[0]:0.001:angles[nA-1] as Julia builds it
   int rows_alloc;       // rows of the shared working matrix (nTE or nTE + nT2)
   int a_elems;          // doubles reserved for the working matrix / EPG scratch per warp
   int copy_elems;       // doubles per TMA bulk copy of one nTE x nT2 matrix (even)
@@ -150,7 +153,8 @@ __constant__ PipeParams cP;
 #define VIEWG(T, name) T *const name = this->name; SHG(name)
 #define VIEW_GWS() const GramWs gws = this->gws; SH(gws.y); SH(gws.s); SH(gws.x); SH(gws.w); SH(gws.t1); SH(gws.t2); SH(gws.P)
 
-template <bool GRAM>
+// LEGACY instantiates the legacy = true searches (legacy.cuh); the default instantiation carries none of that code
+template <bool GRAM, bool LEGACY = false>
 struct Warp {
   long long prof_cyc[PF_COUNT] = {0};
   Src cursrc;
@@ -319,6 +323,69 @@ struct Warp {
     xs = warp_bcast(bestx, 0), us = warp_bcast(bestu, 0);
   }
 
+  // Workspace of the legacy searches in the warp's global scratch: the L-curve / flip-angle tables of the QR port
+  // (ScratchLayout lc_pts .. fa_mask, 768 doubles) are idle whenever these run.  X | Y | t | c | z | a
+  struct LegacyWs {
+    double *X, *Y, *t, *c, *z, *a;
+  };
+  __device__ __forceinline__ LegacyWs legacy_ws() const {
+    double *lw = g + sl.lc_pts;
+    GL(lw);
+    LegacyWs w;
+    w.X = lw, w.Y = lw + 64, w.t = lw + 128, w.c = lw + 196, w.z = lw + 260, w.a = lw + 324;  // 324 + 4*64 = 580 <= 768
+    return w;
+  }
+
+  // suggest_point of CubicSplineSurrogate(...; legacy = true)  src/splines.jl:492-500 -> spline_opt_legacy :419-430
+  __device__ __noinline__ void suggest_point_legacy(unsigned long long seen, double &xs, double &us) {
+    VIEWG(double, fa_u_p);
+    const LegacyWs w = legacy_ws();
+    const int m = __popcll(seen), k = m - 1 < 3 ? m - 1 : 3;
+    if (lane == 0) {
+      int q = 0;
+      for (unsigned long long msk = seen; msk; msk &= msk - 1, q++) {
+        const int I = __ffsll((long long)msk) - 1;
+        w.X[q] = cP.angles[I], w.Y[q] = fa_u_p[I];
+      }
+      fitpack_interp_dev(w.X, w.Y, m, k, w.t, w.c, w.z, w.a);
+    }
+    __syncwarp();
+    legacy_spline_scan(w.t, w.c, m, k, cP.lg_range, 0, 0.0, xs, us);
+  }
+
+  // lsqnonneg_chi2!(...; method = :legacy)  src/lsqnonneg.jl:521-533 with chi2_search_from_minimum :595-636:
+  // mu doubles from 1e-3 until res2(mu) >= Chi2Factor * res2_min, then the sampled root of the spline through every
+  // (mu, res2) seen (mu = 0 included) on the grid 0:0.001:mu_last.  Returns -1 when the doubling does not end
+  // within DECAES_LEGACY_CHI2_MAXPTS points (the reference would keep doubling).
+  __device__ __noinline__ double chi2_legacy(double res2_min, const double *Asrc) {
+    const LegacyWs w = legacy_ws();
+    const double target = __dmul_rn(cP.Chi2Factor, res2_min);
+    int m = 1;
+    if (lane == 0) w.X[0] = 0.0, w.Y[0] = res2_min;
+    double munew = 1e-3;
+    bool ok = false;
+    _Pragma("unroll 1") while (m < DECAES_LEGACY_CHI2_MAXPTS) {
+      cache_solve(munew, Asrc);
+      const double r = cur_resnorm_sq();
+      if (lane == 0) w.X[m] = munew, w.Y[m] = r;
+      m++;
+      if (r >= target) {
+        ok = true;
+        break;
+      }
+      munew *= 2.0;
+    }
+    if (!ok) return -1.0;
+    const int k = m - 1 < 3 ? m - 1 : 3;
+    if (lane == 0) fitpack_interp_dev(w.X, w.Y, m, k, w.t, w.c, w.z, w.a);
+    __syncwarp();
+    LegacyRange r;  // 0.0:0.001:(1e-3 * 2^(m-2)) lifts to the rationals i/1000, i = 0 .. 2^(m-2)
+    r.rational = 1, r.start_n = 0, r.step_n = 1, r.den = 1000, r.len = (1ll << (m - 2)) + 1, r.start = 0.0, r.step = 0.001;
+    double mu, yr;
+    legacy_spline_scan(w.t, w.c, m, k, r, 1, target, mu, yr);
+    return mu;
+  }
+
   // EPG basis at `alpha` for this voxel (+ Gram matrix and right-hand side for the Gram solver)
   __device__ void basis_at(double alpha, long long v) {
     if constexpr (GRAM) {
@@ -355,7 +422,9 @@ struct Warp {
     const int maxeval = cP.maxeval, nA = cP.nA;
     for (int s = 0; s < cP.nseed; s++) fa_probe(cP.seeds[s], seen, numeval);
     double x, u;
-    suggest_point(seen, x, u);
+    unsigned long long seen_sugg = 0ull;  // legacy: the scan is expensive, skip it when nothing new was probed
+    if constexpr (LEGACY) suggest_point_legacy(seen, x, u), seen_sugg = seen;
+    else suggest_point(seen, x, u);
     while (true) {
       // minimal_bounding_box :778-800
       int lo = 0, hi = nA - 1;
@@ -381,7 +450,8 @@ struct Warp {
           if (numeval >= maxeval) break;
         }
       }
-      suggest_point(seen, x, u);
+      if constexpr (!LEGACY) suggest_point(seen, x, u);
+      else if (seen != seen_sugg) suggest_point_legacy(seen, x, u), seen_sugg = seen;
       if (numeval >= maxeval || (hi - lo) <= 1) break;
     }
     return x;
@@ -1535,6 +1605,23 @@ struct Warp {
           // the reference's save_results! reads a stale cache slot here (src/lsqnonneg.jl:465, 657);
           // we return the value the chooser itself returns and count the voxel
           n_early++;
+        } else if (LEGACY && cP.reg == 3) {
+          if constexpr (LEGACY) {
+            cache_reset();
+            mu = chi2_legacy(res2_min, Asrc);
+            if (!(mu > 0.0)) {
+              // mu == 0: x_final = x_unreg (:528-529) and f(0) = res2_min, so chi2 = 1; mu < 0 flags a doubling
+              // search that did not end (the reference would keep doubling): reported as NaN.  Both are counted.
+              chi2 = (mu == 0.0) ? 1.0 : CUDART_NAN;
+              if (mu < 0.0) mu = CUDART_NAN;
+              n_early++;
+              solve_unreg(Asrc);
+            } else {
+              cache_solve(mu, Asrc);  // a cache hit: f(mu_final) was the last solve
+              chi2 = cur_resnorm_sq() / res2_min;
+              src_kind = 1;
+            }
+          }
         } else {
           cache_reset();
           double xf, ff;

@@ -126,8 +126,9 @@ end
 
 # Route the public Float64 entry points through the GPU library (the two-line patch a maintainer
 # would apply inside DECAES itself is shown in INTEGRATION.md).
+# `legacy = true` (sampled FITPACK spline for the flip angle and for the chi2 root, src/splines.jl:419-446,
+# src/lsqnonneg.jl:595-636) runs on the GPU as well; Float32 volumes keep DECAES.jl's generic CPU method.
 DECAES.T2mapSEcorr!(maps::T2Maps{Float64}, dist::T2Distributions{Float64}, image::Array{Float64, 4}, opts::T2mapOptions{Float64}) =
-    opts.legacy ? invoke(DECAES.T2mapSEcorr!, Tuple{T2Maps, T2Distributions, Array{T, 4}, T2mapOptions{T}} where {T}, maps, dist, image, opts) :
     t2map_gpu!(maps, dist, image, opts)
 
 DECAES.T2partSEcorr(T2distributions::Array{Float64, 4}, opts::T2partOptions{Float64}) = t2part_gpu(T2distributions, opts)

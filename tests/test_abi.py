@@ -66,8 +66,9 @@ def test_validation_through_the_abi(pkg, orc):
     assert b"four echoes" in L.decaes_last_error()
     bad = orc.make_t2map_opts((nvox, 1, 1), 32, 40, 10e-3, Reg="chi2")  # Chi2Factor unset
     assert L.decaes_t2map(img.ctypes.data, C.byref(bad), None, C.byref(out)) == -1
-    leg = orc.make_t2map_opts((nvox, 1, 1), 32, 40, 10e-3, legacy=True)
-    assert L.decaes_t2map(img.ctypes.data, C.byref(leg), None, C.byref(out)) == -3
+    big = orc.make_t2map_opts((nvox, 1, 1), 32, 65, 10e-3)  # nT2 > 64: outside the accelerated path
+    assert L.decaes_t2map(img.ctypes.data, C.byref(big), None, C.byref(out)) == -3
+    assert b"nT2 > 64" in L.decaes_last_error()
     good = orc.make_t2map_opts((nvox, 1, 1), 32, 40, 10e-3)
     noout = pkg._abi.T2mapOut()
     assert L.decaes_t2map(img.ctypes.data, C.byref(good), None, C.byref(noout)) == -1

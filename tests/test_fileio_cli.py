@@ -112,8 +112,9 @@ def test_cli_parsing_settings_file_and_reg_params(cli, tmp_path):
         cli.parse_cli(["x.mat"])
     with pytest.raises(AssertionError, match="Must set chi2 factor"):
         cli.parse_cli(["x.mat", "--T2map", "--Reg", "chi2"])
-    with pytest.raises(SystemExit):
-        cli.parse_cli(["x.mat", "--T2map", "--legacy"])
+    with pytest.warns(UserWarning, match="--legacy is deprecated"):  # warn_deprecated_future_removed  src/main.jl:441-443
+        o = cli.parse_cli(["x.mat", "--T2map", "--legacy"])
+    assert o["legacy"] is True
 
 
 def test_cli_file_infos_rules(cli, tmp_path):

@@ -57,6 +57,38 @@ def test_gpu_matches_oracle(pkg, orc, name, nTE, TE, nT2, Reg, extra, part_kw, n
     assert stats["voxels_processed"] == nvox and stats["kernel_launches"] >= 2
 
 
+# legacy = true (src/types.jl:20-21, 59-63): every angle of an 8-point grid is probed, the flip angle is the sampled
+# minimum of the FITPACK spline (src/splines.jl:419-430) and Reg = chi2 runs the doubling search with the sampled
+# spline root (src/lsqnonneg.jl:595-636).  Both answers live on a 0.001 grid, so parity is exact or one grid step.
+@pytest.mark.parametrize("Reg,extra,nA,nAmin", [("none", {}, 8, 8), ("chi2", {"Chi2Factor": 1.02}, 8, 8),
+                                                ("lcurve", {}, 8, 8), ("chi2", {"Chi2Factor": 1.05}, 16, 5)])
+def test_legacy_algorithms(pkg, orc, Reg, extra, nA, nAmin):
+    nvox, nTE, nT2, TE = 384, 32, 40, 10e-3
+    img = orc.mock_image(nvox, nTE, TE, seed=21)
+    o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, TE, Reg=Reg, legacy=True, nRefAngles=nA, nRefAnglesMin=nAmin,
+                            ngpus=1, **extra)
+    p = orc.make_t2part_opts((nvox, 1, 1), nT2)
+    ref, st = orc.t2map(img, o, p)
+    got = gpu_t2map(pkg, orc, img, o, p)
+    da = np.abs(got["alpha"] - ref["alpha"])
+    print("legacy", Reg, "alpha: exact", int((da == 0).sum()), "one step", int(((da > 0) & (da < 1.5e-3)).sum()),
+          "max", da.max(), "oracle early returns", st.early_returns)
+    assert np.all(np.round(got["alpha"] * 1000) / 1000 == got["alpha"])  # a sample of knots[1]:0.001:knots[end]
+    assert (da == 0).mean() >= 0.99 and da.max() < 1.5e-3
+    same = da == 0
+    if Reg == "chi2":
+        dm = np.abs(got["mu"] - ref["mu"])
+        assert np.all(np.round(got["mu"] * 1000) / 1000 == got["mu"])
+        assert (dm[same] == 0).mean() >= 0.99 and dm[same].max() < 1.5e-3
+        same &= dm == 0
+    rep = parity.compare({k: v[same] for k, v in ref.items()}, {k: v[same] for k, v in got.items()})
+    print(rep)
+    assert rep["nan_mismatch"] == 0
+    assert rep["frac_out_of_tolerance_same_mu"] <= 0.02, rep
+    assert rep["mu_flip_frac"] <= (0.08 if Reg == "lcurve" else 0.0), rep
+    assert pkg.last_stats()["voxels_processed"] == nvox
+
+
 def test_optional_outputs_and_threshold(pkg, orc):
     nvox, nTE, nT2, TE = 512, 32, 40, 10e-3
     img = orc.mock_image(nvox, nTE, TE, seed=11)

@@ -146,8 +146,8 @@ def test_option_validation(orc):
         args = {**base, **kw}
         o = orc.make_t2map_opts(args.pop("shape"), args.pop("nTE"), args.pop("nT2"), args.pop("TE"), **args)
         assert L.orc_validate_t2map_opts(C.byref(o), msg, 256) == -1, kw
-    o = orc.make_t2map_opts((2, 2, 2), 32, 40, 10e-3, legacy=True)
-    assert L.orc_validate_t2map_opts(C.byref(o), msg, 256) == -3
+    o = orc.make_t2map_opts((2, 2, 2), 32, 40, 10e-3, legacy=True, nRefAngles=8, nRefAnglesMin=8)
+    assert L.orc_validate_t2map_opts(C.byref(o), msg, 256) == 0
 
 
 def test_thread_count_does_not_change_results(orc, image):

@@ -2,7 +2,7 @@
 """SASS instruction count of every out-of-line device function of voxel_pipeline_kernel<true>."""
 import re, subprocess, sys
 so = sys.argv[1] if len(sys.argv) > 1 else "decaes.jl_b200/libdecaes_cuda.so"
-kern = sys.argv[2] if len(sys.argv) > 2 else "voxel_pipeline_kernelILb1"
+kern = sys.argv[2] if len(sys.argv) > 2 else "voxel_pipeline_kernelILb1ELb0E"
 elf = subprocess.run(["cuobjdump", "-elf", so], capture_output=True, text=True).stdout
 rows = []
 for line in elf.splitlines():

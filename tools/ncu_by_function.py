@@ -8,7 +8,7 @@ Reads the SASS source page of the report, the symbol table of the cubin embedded
 import collections, csv, re, subprocess, sys
 
 rep, so = sys.argv[1], sys.argv[2]
-kern = sys.argv[3] if len(sys.argv) > 3 else "voxel_pipeline_kernelILb1"
+kern = sys.argv[3] if len(sys.argv) > 3 else "voxel_pipeline_kernelILb1ELb0E"
 elf = subprocess.run(["cuobjdump", "-elf", so], capture_output=True, text=True).stdout
 syms = []
 for line in elf.splitlines():
