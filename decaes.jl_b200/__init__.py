@@ -60,6 +60,7 @@ def lib():
         L.decaes_mock_image_device.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_double,
                                                C.c_double, C.c_uint64, vp]
         L.decaes_get_stats.argtypes = [C.POINTER(RunStats)]
+        L.decaes_release.restype = None
         L.decaes_measure_fp64_peak.argtypes = [dp]
         L.decaes_slab_bounds.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         for name in _abi.DECLARED_SYMBOLS:
@@ -81,6 +82,11 @@ def last_stats():
     st = RunStats()
     lib().decaes_get_stats(C.byref(st))
     return {name: getattr(st, name) for name, _ in RunStats._fields_}
+
+
+def release():
+    """Give back the device workspaces the library caches between calls (decaes_release)."""
+    lib().decaes_release()
 
 
 # ------------------------------------------------------------------------------------ options

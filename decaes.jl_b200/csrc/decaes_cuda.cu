@@ -605,8 +605,9 @@ static int make_part_tables(const decaes_t2part_opts *o, PartTables *t) {
 // ---- per-device workspace (grow-only, cached across calls) ----
 struct DeviceWs {
   double *basis_rm = nullptr, *basis_cm = nullptr, *dbasis_cm = nullptr, *scratch = nullptr, *gram_set = nullptr;
+  double *slab = nullptr;  // host API: device copy of this device's voxel slab (image + outputs), kept between calls
   unsigned long long *counters = nullptr;
-  size_t basis_rm_cap = 0, basis_cm_cap = 0, scratch_cap = 0, gram_cap = 0;
+  size_t basis_rm_cap = 0, basis_cm_cap = 0, scratch_cap = 0, gram_cap = 0, slab_cap = 0;
   size_t l2_persist_max = 0, l2_window_max = 0;  // persisting-L2 carve-out set aside for the scratch, largest access-policy window
   bool props_known = false;
   cudaDeviceProp prop;
@@ -1070,6 +1071,8 @@ int decaes_setup_tables(const decaes_t2map_opts *o, double *echotimes, double *t
 }
 
 // ---------------------------------------------------------------------------- host-pointer API
+static std::mutex g_call_mutex;  // re-entrant host calls are serialised
+static std::mutex &g_call_mutex_fwd() { return g_call_mutex; }
 struct SlabJob {
   int dev;
   int64_t v0, v1;
@@ -1106,8 +1109,18 @@ static int run_slab(SlabJob &job, const double *image, int64_t Nvox, const decae
     off[f] = total;
     if (hostp[f]) total += (size_t)nv * mult[f];
   }
+  // The slab buffer is cached per device (grow-only, like the other workspaces): cudaMalloc + cudaFree of the 5.5 GB
+  // of a full cfg3 volume cost more than the exposed copies.  decaes_release() or DECAES_SLAB_CACHE=0 give it back.
+  static const bool cache_slab = !(getenv("DECAES_SLAB_CACHE") && atoi(getenv("DECAES_SLAB_CACHE")) == 0);
   double *dbuf = nullptr;
-  CUDA_TRY(cudaMalloc(&dbuf, total * sizeof(double)));
+  if (cache_slab) {
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    DeviceWs &ws = g_ws[job.dev];
+    if ((rc = ensure(&ws.slab, &ws.slab_cap, total))) return rc;
+    dbuf = ws.slab;
+  } else {
+    CUDA_TRY(cudaMalloc(&dbuf, total * sizeof(double)));
+  }
   decaes_t2map_out dout;
   double **dptr = (double **)&dout;
   for (int f = 0; f < 16; f++) dptr[f] = hostp[f] ? dbuf + off[f] : nullptr;
@@ -1160,13 +1173,33 @@ static int run_slab(SlabJob &job, const double *image, int64_t Nvox, const decae
   rc = collect_device_stats(job.dev, &job.st);
   cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2), cudaEventDestroy(e3);
   for (int c = 0; c < nchunks; c++) cudaEventDestroy(evin[c]), cudaEventDestroy(evdone[c]);
-  cudaFree(dbuf);
+  if (!cache_slab) cudaFree(dbuf);
   cudaStreamDestroy(sc);
   cudaStreamDestroy(st);
   return rc;
 }
 
-static std::mutex g_call_mutex;  // re-entrant host calls are serialised
+void decaes_release(void) {
+  std::lock_guard<std::mutex> lk(g_call_mutex_fwd());
+  std::lock_guard<std::mutex> lk2(g_ws_mutex);
+  int cur = 0, ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  cudaGetDevice(&cur);
+  for (int d = 0; d < ndev && d < 64; d++) {
+    DeviceWs &ws = g_ws[d];
+    if (!(ws.slab || ws.scratch || ws.basis_rm || ws.basis_cm || ws.gram_set)) continue;
+    cudaSetDevice(d);
+    cudaDeviceSynchronize();
+    cudaFree(ws.slab), cudaFree(ws.scratch), cudaFree(ws.basis_rm), cudaFree(ws.basis_cm), cudaFree(ws.dbasis_cm), cudaFree(ws.gram_set);
+    ws.slab = ws.scratch = ws.basis_rm = ws.basis_cm = ws.dbasis_cm = ws.gram_set = nullptr;
+    ws.slab_cap = ws.scratch_cap = ws.basis_rm_cap = ws.basis_cm_cap = ws.gram_cap = 0;
+  }
+  cudaSetDevice(cur);
+}
+
 
 int decaes_t2map(const double *image, const decaes_t2map_opts *opts, const decaes_t2part_opts *part,
                  const decaes_t2map_out *out) {

@@ -46,7 +46,7 @@ typedef enum {
   DECAES_OK = 0,
   DECAES_EINVAL = -1,       /* option fails a T2mapOptions/T2partOptions assertion (src/types.jl:28-84,148-168) */
   DECAES_ECUDA = -2,        /* CUDA runtime error / no device */
-  DECAES_EUNSUPPORTED = -3, /* feature outside the hot path (legacy=true) */
+  DECAES_EUNSUPPORTED = -3, /* size outside the accelerated path (nT2 > 64, nRefAngles > 64, nTE > 72) */
   DECAES_ENOMEM = -4
 } decaes_status;
 
@@ -67,7 +67,7 @@ typedef struct {
   int32_t nRefAngles;      /* default 64                                    */
   int32_t nRefAnglesMin;   /* default min(5, nRefAngles)                    */
   int32_t reg;             /* decaes_reg                                    */
-  int32_t legacy;          /* must be 0                                     */
+  int32_t legacy;          /* legacy = true algorithms (src/types.jl:20-21)  */
   int32_t alpha_provided;  /* out->alpha holds a B1 map on entry (src/T2mapSEcorr.jl:220-225) */
   int32_t ngpus;           /* host API only: 0 = all visible devices        */
   int32_t reserved;
@@ -157,6 +157,9 @@ const char *decaes_last_error(void);
 int decaes_device_count(void);
 int decaes_abi_version(void);
 void decaes_get_stats(decaes_run_stats *stats);
+/* Frees the device workspaces the library keeps between calls (basis tables, per-warp scratch and, for the host
+ * API, the device copy of each GPU's voxel slab).  They are grow-only caches; the next call re-allocates. */
+void decaes_release(void);
 /* Measured DFMA peak of the current device in FLOP/s (independent FMA chains on all SMs). */
 int decaes_measure_fp64_peak(double *flops_per_s);
 

@@ -280,3 +280,41 @@ def test_full_size_properties(pkg, orc):
     # checksum of checksums against a second identical run: the pipeline is deterministic
     c = run(img)
     assert torch.equal(c["dist"], a["dist"])
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("Reg,extra", [("none", {}), ("lcurve", {}), ("chi2", {"Chi2Factor": 1.02}), ("gcv", {}),
+                                       ("mdp", {"NoiseLevel": 1e-3})])
+def test_pathological_voxels_terminate_and_stay_local(pkg, orc, Reg, extra):
+    """NaN / Inf echoes, an all-zero tail, denormal-scale and 1e300-scale signals, negative and sign-flipped echoes,
+    a constant signal: every search in the kernel is bounded, so the call returns; voxels are independent, so the
+    ordinary voxels around them are bit-identical to a run without the pathological ones; where the oracle's
+    result is finite the GPU agrees on the scale-free maps."""
+    nvox, nTE, nT2, TE = 256, 32, 40, 10e-3
+    clean = orc.mock_image(nvox, nTE, TE, seed=9)
+    img = clean.copy()
+    img[3, 5] = np.nan
+    img[4, 10] = np.inf
+    img[5, 1:] = 0.0
+    img[6, :] = 1e-300 * clean[6, :]
+    img[7, :] = 1e300 * clean[7, :]
+    img[8, 2] = -5.0
+    img[9, :] = img[9, 0]
+    img[10, 1:] = -img[10, 1:]
+    bad = np.arange(3, 11)
+    o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, TE, Reg=Reg, ngpus=1, **extra)
+    p = orc.make_t2part_opts((nvox, 1, 1), nT2)
+    got = gpu_t2map(pkg, orc, img, o, p)
+    base = gpu_t2map(pkg, orc, clean, o, p)
+    ok = np.setdiff1d(np.arange(nvox), bad)
+    for k in ("alpha", "gdn", "ggm", "sfr", "dist"):
+        np.testing.assert_array_equal(got[k][ok], base[k][ok], err_msg=k)
+    ref, _ = orc.t2map(img, o, p)
+    assert pkg.last_stats()["voxels_processed"] == nvox
+    # the flip-angle search never sees the regulariser: same angle wherever the oracle's is well defined
+    for v in (6, 7, 9):
+        assert abs(got["alpha"][v] - ref["alpha"][v]) <= 1e-6, (v, got["alpha"][v], ref["alpha"][v])
+    if Reg in ("none", "lcurve"):
+        assert np.isnan(got["gdn"][4]) == np.isnan(ref["gdn"][4])
+        for v in (6, 7):  # power-of-ten scalings: scale-free maps equal those of the unscaled voxel
+            assert abs(got["ggm"][v] - base["ggm"][v]) <= 1e-6 * max(1.0, abs(base["ggm"][v])) or Reg == "lcurve"

@@ -10,7 +10,7 @@ import collections, csv, os, re, subprocess, sys, tempfile
 rep, so = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 60
 filt = sys.argv[4] if len(sys.argv) > 4 else ""
-kern = "voxel_pipeline_kernelILb1ELb0E"
+kern = os.environ.get("KERN", "voxel_pipeline_kernelILb1ELb0E")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
