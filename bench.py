@@ -81,6 +81,12 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_name(wl_name):
+    """config.workload — the same string on both arms (ours and --impl reference)."""
+    shape, nTE, TE, nT2, Reg, extra = WORKLOADS[wl_name]
+    return f"{wl_name}: {nTE}-echo {'x'.join(map(str, shape))}, nT2={nT2}, Reg={Reg} + T2part"
+
+
 def oracle_sample(orc, wl, nvox, seed, threads):
     """Run the CPU oracle on `nvox` voxels of the workload; returns (voxels/s, flops/voxel, stats)."""
     shape, nTE, TE, nT2, Reg, extra = wl
@@ -91,7 +97,7 @@ def oracle_sample(orc, wl, nvox, seed, threads):
     return nvox / st.seconds, st.flops / max(st.voxels_processed, 1), st
 
 
-def run_reference(args, wl_name):
+def run_reference(args, wl_name, out):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  DECAES.jl
     is Julia and cannot run in this image, so this is the oracle port (kind = "port")."""
     rank = int(os.environ.get("RANK", "0"))
@@ -115,17 +121,28 @@ def run_reference(args, wl_name):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{wl_name}: {nTE}-echo {'x'.join(map(str, shape))}, nT2={nT2}, Reg={Reg} (+T2part)",
-                   "sample_voxels_per_step": sample},
+        "config": {"workload": workload_name(wl_name), "sample_voxels_per_step": sample,
+                   "note": "each step is a bounded sample of the workload on all host cores"},
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} voxels of the same synthetic workload per step, OpenMP C restatement of DECAES.jl (no Julia runtime in the image)"},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner on
+    init), so everything else is routed to stderr at the file-descriptor level and the JSON line goes to the
+    original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    out = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -140,7 +157,7 @@ def main():
     args = ap.parse_args()
 
     if args.impl == "reference":
-        run_reference(args, args.workload)
+        run_reference(args, args.workload, out)
         return
 
     import torch
@@ -302,7 +319,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {nTE}-echo {'x'.join(map(str, shape))}, nT2={nT2}, Reg={Reg} (+fused T2part), one volume per rank",
+            "config": {"workload": workload_name(args.workload), "sharding": "one volume per rank, T2part fused into the same kernel",
                        "voxels_per_rank": nvox, "l2": "inputs+outputs per step exceed L2 (no flush needed)",
                        "debug_voxels_override": bool(args.voxels)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * args.steps,  # basis_setup + gram_setup + voxel_pipeline per step
@@ -310,7 +327,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "one_volume_all_gpus": one_volume,
             "voxels_processed_last_step": processed, "checksum_gdn": checksum,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -12,7 +12,9 @@
 #define DECAES_LC_MAX 64       // L-curve point / state cache capacity per voxel
 #define DECAES_NCACHE 8        // NNLSTikhonovRegProblemCache slots (src/lsqnonneg.jl:396)
 #define DECAES_GROUP 4         // voxels fetched per work item = one 32-byte sector per echo
+#ifndef DECAES_MAX_WARPS
 #define DECAES_MAX_WARPS 12    // warps per persistent CTA (register file: 65536 / (12*32) = 170 regs/thread)
+#endif
 
 namespace decaes {
 

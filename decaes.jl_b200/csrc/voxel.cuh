@@ -128,6 +128,11 @@ struct Src {               // where the current basis of the Gram solver lives
   const double *Acm;       // column-major [col * nTE + i]
 };
 
+#define DECAES_PRAGMA_(x) _Pragma(#x)
+#define DECAES_PRAGMA(x) DECAES_PRAGMA_(x)
+#ifndef DECAES_EPG_UNROLL
+#define DECAES_EPG_UNROLL 1  // state loop of the shared-memory EPG (independent iterations: unrolling buys ILP, costs code)
+#endif
 #ifdef DECAES_PROFILE
 #define PROF_BEGIN(id) long long prof_t0_##id = clock64()
 #define PROF_END(id) prof_cyc[id] += clock64() - prof_t0_##id
@@ -515,7 +520,7 @@ struct Warp {
         }
         ST(0, 1) = vFb, ST(2, 1) = vZ;
         double pend = vF;
-        _Pragma("unroll 1") for (int k = 2; k <= kmax; k++) {
+        DECAES_PRAGMA(unroll DECAES_EPG_UNROLL) for (int k = 2; k <= kmax; k++) {
           F = ST(0, k), Fb = ST(1, k), Z = ST(2, k);
           ST(0, k) = pend;
           UPD();

@@ -25,6 +25,7 @@ CONFIGS = [
 
 
 def gpu_t2map(pkg, orc, img, o, p, **alloc_kw):
+    img = np.asfortranarray(img, dtype=np.float64)  # (nvox, nTE) column-major: voxel v, echo e at v + e*nvox
     nvox, nTE = img.shape
     arrs, out = orc.alloc_outputs(nvox, nTE, o.nT2, part=p is not None, **alloc_kw)
     L = pkg.lib()
@@ -292,7 +293,7 @@ def test_pathological_voxels_terminate_and_stay_local(pkg, orc, Reg, extra):
     result is finite the GPU agrees on the scale-free maps."""
     nvox, nTE, nT2, TE = 256, 32, 40, 10e-3
     clean = orc.mock_image(nvox, nTE, TE, seed=9)
-    img = clean.copy()
+    img = clean.copy(order="F")  # (nvox, nTE) column-major = Julia's [echo][voxel] memory order
     img[3, 5] = np.nan
     img[4, 10] = np.inf
     img[5, 1:] = 0.0
