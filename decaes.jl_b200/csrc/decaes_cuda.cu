@@ -199,13 +199,13 @@ __global__ void gram_setup_kernel(const __grid_constant__ SetupParams S, double 
 // instruction-fetch bound (ncu: stall_no_inst dominates when warps wander through the ~100 KB of hot
 // code independently; every phase runs 10-20 % slower when phases overlap), and warps that execute
 // the same phase share its cache lines.
-template <bool GRAM, bool LEGACY = false>
+template <bool GRAM, bool LEGACY = false, int VS = 64>
 __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kernel(const __grid_constant__ PipeParams P) {
   extern __shared__ __align__(128) double smem[];
   const int wid = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + wid;
   double *gscratch = P.scratch + (size_t)gwarp * P.scratch_per_warp;
-  Warp<GRAM, LEGACY> W(P, smem + (size_t)wid * (P.smem_per_warp / 8), gscratch);
+  Warp<GRAM, LEGACY, VS> W(P, smem + (size_t)wid * (P.smem_per_warp / 8), gscratch);
   const int lane = lane_id();
   if (lane == 0) {
     mbar_init(W.bar, 1);
@@ -602,6 +602,14 @@ static int make_part_tables(const decaes_t2part_opts *o, PartTables *t) {
   return DECAES_OK;
 }
 
+// the instantiation that serves a parameter set: solver variant x legacy searches x vector stride of the Gram solver
+typedef void (*pipeline_kernel_t)(const PipeParams);
+static pipeline_kernel_t pipeline_kernel_for(const PipeParams &P) {
+  if (!P.gram) return voxel_pipeline_kernel<false, false, 64>;
+  if (P.legacy) return P.gv_stride == 40 ? voxel_pipeline_kernel<true, true, 40> : voxel_pipeline_kernel<true, true, 64>;
+  return P.gv_stride == 40 ? voxel_pipeline_kernel<true, false, 40> : voxel_pipeline_kernel<true, false, 64>;
+}
+
 // ---- per-device workspace (grow-only, cached across calls) ----
 struct DeviceWs {
   double *basis_rm = nullptr, *basis_cm = nullptr, *dbasis_cm = nullptr, *scratch = nullptr, *gram_set = nullptr;
@@ -711,6 +719,8 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
 
   // Shared memory per warp decides how many voxels an SM holds.  Moving the two coldest per-voxel tables (cached
   // solutions, L-curve state records) to the warp's global scratch costs ~1 % each and is done when it buys a warp.
+  // stride of the solver's vectors: 40 covers the reference's default nT2 = 40 and buys a 12th warp on configs 1-3
+  P.gv_stride = (P.gram && nT2 <= 40 && !getenv("DECAES_GV_STRIDE_64")) ? 40 : 64;
   P.spill = 0;
   if (P.gram) {
     int optin = 0;
@@ -718,14 +728,14 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     int best_w = 0;
     bool best_epg = false;
     for (int sp : {0, 1, 3}) {
-      SmemLayout Ls(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, sp);
+      SmemLayout Ls(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, sp, P.gv_stride);
       int w = (int)std::min<size_t>(DECAES_MAX_WARPS, ((size_t)optin - 1024) / Ls.total_bytes);
       const bool epg_ok = 3 * P.epg_kmax * (P.epg_lanes + 1) <= Ls.bd;  // the shared-memory EPG must still fit in front of the signal
       if ((epg_ok && !best_epg && w >= 1) || (epg_ok == best_epg && w > best_w)) best_w = w, best_epg = epg_ok, P.spill = sp;
     }
     if (const char *e = getenv("DECAES_SPILL")) P.spill = atoi(e) & 3;
   }
-  SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, P.spill);
+  SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, P.spill, P.gv_stride);
   plan->smem_bytes = L.total_bytes;
   // the solver block + search caches (everything in front of the voxel's signal) are idle while the basis is built
   P.epg_smem = P.gram && 3 * P.epg_kmax * (P.epg_lanes + 1) <= L.bd;
@@ -760,12 +770,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.warps_per_cta = wpc, P.smem_per_warp = plan->smem_bytes;
   plan->warps_per_cta = wpc;
   plan->cta_smem = wpc * plan->smem_bytes;
-  if (P.legacy)
-    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
-  else if (P.gram)
-    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
-  else
-    CUDA_TRY(cudaFuncSetAttribute(voxel_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
+  CUDA_TRY(cudaFuncSetAttribute(pipeline_kernel_for(P), cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
   plan->grid = prop.multiProcessorCount;
 
   ScratchLayout sl(nTE, nT2, P.copy_elems, o->reg == DECAES_REG_GCV);
@@ -855,12 +860,7 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
     window = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
     if (!window) cudaGetLastError();
   }
-  if (P.legacy)
-    voxel_pipeline_kernel<true, true><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
-  else if (P.gram)
-    voxel_pipeline_kernel<true><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
-  else
-    voxel_pipeline_kernel<false><<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
+  pipeline_kernel_for(P)<<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   if (window) {
     cudaStreamAttrValue attr;

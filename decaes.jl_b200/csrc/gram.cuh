@@ -24,7 +24,7 @@
 // lane-parallel symmetric elimination (gram_factor) instead of k sequential appends.
 //
 // Shared-memory layout of one warp (doubles, relative to V):
-//     c[64] y[64] s[64] t1[64] t2[64] x[64] w[64] P[64 ints]  T[n x ld]
+//     c[VS] y[VS] s[VS] t1[VS] t2[VS] x[VS] w[VS] P[VS ints]  T[n x ld]      (VS = 40 or 64 >= n)
 // T (ld = (n+1)|1, odd => both access directions are bank-conflict free) holds the lower triangle
 // of G and, in the strictly-upper part, M:
 //     G(p,q) = T[max(p,q)*ld + min(p,q)]          M(t,u) = T[u*ld + t + 1]   (u <= t)
@@ -50,7 +50,13 @@ __device__ unsigned long long g_solve_hist[3][48];  // per solve index within a 
 #define GP_ADD(id, v)
 #endif
 
-enum { GV_C = 0, GV_Y = 64, GV_S = 128, GV_T1 = 192, GV_T2 = 256, GV_X = 320, GV_W = 384, GV_P = 448, GV_T = 480 };
+// VS = vector stride: 40 when nT2 <= 40 (the reference's default grid; 1.4 KB less shared memory per warp than a
+// stride of 64, which is what lets a 12th warp fit on the SM for the benchmark configs), 64 otherwise.  It is a
+// template parameter of the solver so that every offset stays an immediate.
+#define GV_LAYOUT(VS)                                                                                             \
+  enum { GV_C = 0, GV_Y = (VS), GV_S = 2 * (VS), GV_T1 = 3 * (VS), GV_T2 = 4 * (VS), GV_X = 5 * (VS), GV_W = 6 * (VS), \
+         GV_P = 7 * (VS), GV_T = 7 * (VS) + (VS) / 2 }
+__host__ __device__ constexpr int gv_block_doubles(int vs) { return 7 * vs + vs / 2; }  // vectors + pivot list, in front of G / M
 
 struct GramOut {
   int k;                     // number of active columns
@@ -103,7 +109,9 @@ __device__ __forceinline__ unsigned long long dkey(double x) {
 // Append column j to the factorisation at pivot position k.  Returns false (and changes nothing)
 // when the column is numerically dependent (d^2 <= 0) or, with `need_positive`, when its
 // coefficient would not be positive (the reference's b1/A1 > 0 test).  The caller increments k.
+template <int VS>
 __device__ __noinline__ bool gram_append(double *V, int ld, int k, int j, double mu2, bool need_positive) {
+  GV_LAYOUT(VS);
   __builtin_assume(__isShared(V));
   const int lane = lane_id();
   double *T = V + GV_T;
@@ -166,7 +174,9 @@ __device__ __noinline__ bool gram_append(double *V, int ld, int k, int j, double
 // pipeline: the kernel is instruction-fetch bound and straight-line code has no reuse.)
 // Returns false when a pivot is not positive (numerically dependent set): the caller falls back
 // to sequential appends, which drop the offending column.
+template <int VS>
 __device__ __noinline__ bool gram_factor(double *V, int ld, int k, double mu2) {
+  GV_LAYOUT(VS);
   __builtin_assume(__isShared(V));
   const int lane = lane_id();
   const int r0 = lane >> 2, c0 = lane & 3;
@@ -226,8 +236,10 @@ __device__ __noinline__ bool gram_factor(double *V, int ld, int k, double mu2) {
 }
 
 // (Re)build the factorisation of the columns listed in P[0:k).  Returns the number of columns kept.
+template <int VS>
 __device__ __noinline__ int gram_refactor(double *V, int ld, int k, double mu2) {
-  if (k == 0 || gram_factor(V, ld, k, mu2)) return k;
+  GV_LAYOUT(VS);
+  if (k == 0 || gram_factor<VS>(V, ld, k, mu2)) return k;
   // numerically dependent set (rare): sequential appends, dropping the offending columns
   GP_ADD(15, 1);
   int *P = (int *)(V + GV_P);
@@ -235,7 +247,7 @@ __device__ __noinline__ int gram_refactor(double *V, int ld, int k, double mu2) 
   for (int t = 0; t < k; t++) {
     const int j = P[t];
     __syncwarp();
-    if (gram_append(V, ld, kk, j, mu2, false)) {
+    if (gram_append<VS>(V, ld, kk, j, mu2, false)) {
       kk++;
     } else {
       if (lane_id() == 0) V[GV_X + j] = 0.0;
@@ -252,7 +264,9 @@ __device__ __noinline__ int gram_refactor(double *V, int ld, int k, double mu2) 
 // rotation touches only the lane's own two entries, the rotation coefficients follow from column r
 // alone and are computed redundantly by every lane; lane r (whose column disappears) carries y.
 // The caller compacts P and recomputes s (gram_solve_s) once all removals are done.
+template <int VS>
 __device__ __noinline__ void gram_downdate(double *V, int ld, int k, int r) {
+  GV_LAYOUT(VS);
   __builtin_assume(__isShared(V));
   const int lane = lane_id();
   double *T = V + GV_T;
@@ -282,7 +296,9 @@ __device__ __noinline__ void gram_downdate(double *V, int ld, int k, int r) {
 }
 
 // s = M'y for the current factorisation
+template <int VS>
 __device__ __forceinline__ void gram_solve_s(double *V, int ld, int k) {
+  GV_LAYOUT(VS);
   const int lane = lane_id();
   double *T = V + GV_T;
   _Pragma("unroll 1") for (int u = lane; u < k; u += 32) {
@@ -296,13 +312,15 @@ __device__ __forceinline__ void gram_solve_s(double *V, int ld, int k) {
 // Remove pivot position imv, then any other non-positive coefficient (first found), compacting P
 // (src/NNLS.jl:735-778); the factorisation follows by Givens downdates (k <= 32) or is rebuilt.
 // Returns the new number of active columns; s is up to date on return.
+template <int VS>
 __device__ __noinline__ int gram_remove(double *V, int ld, int k, int imv, double mu2) {
+  GV_LAYOUT(VS);
   __builtin_assume(__isShared(V));
   const int lane = lane_id();
   int *P = (int *)(V + GV_P);
   const bool small = k <= 32;
   while (true) {
-    if (small) gram_downdate(V, ld, k, imv);
+    if (small) gram_downdate<VS>(V, ld, k, imv);
     int pn = 0;
     if (lane >= imv && lane < k - 1) pn = P[lane + 1];
     if (lane == 0) V[GV_X + P[imv]] = 0.0;
@@ -323,15 +341,17 @@ __device__ __noinline__ int gram_remove(double *V, int ld, int k, int imv, doubl
     imv = (int)bad;
   }
   if (small) {
-    gram_solve_s(V, ld, k);
+    gram_solve_s<VS>(V, ld, k);
     return k;
   }
-  return gram_refactor(V, ld, k, mu2);
+  return gram_refactor<VS>(V, ld, k, mu2);
 }
 
 // Lawson–Hanson main loop.  cold: start from the empty set with the reference's warm dual
 // (src/lsqnonneg.jl:44-70).  warm: start from the feasible point x supported on `mask`.
+template <int VS>
 __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, int max_set, bool warm, unsigned long long mask) {
+  GV_LAYOUT(VS);
   __builtin_assume(__isShared(V));
   const int lane = lane_id();
   double *T = V + GV_T;
@@ -371,7 +391,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
       }
     __syncwarp();
     const int kk = __popcll(mask);
-    k = gram_refactor(V, ld, kk, mu2);
+    k = gram_refactor<VS>(V, ld, kk, mu2);
     if (k != kk) mask = mask_of(P, k);  // a column was dropped as dependent
     check_first = (k > 0);
     if (k == 0) {
@@ -396,7 +416,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
       unsigned long long best;
       bj = warp_argmax_bits(key, bj, best);
       if (best == 0ull) break;  // no positive dual left: KKT point
-      if (!gram_append(V, ld, k, bj, mu2, true)) {
+      if (!gram_append<VS>(V, ld, k, bj, mu2, true)) {
         if (lane == 0) V[GV_W + bj] = 0.0;  // rejected (src/NNLS.jl:652-657)
         __syncwarp();
         continue;
@@ -434,7 +454,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
         V[GV_X + jx] = fma(al, V[GV_S + t] - V[GV_X + jx], V[GV_X + jx]);
       }
       __syncwarp();
-      k = gram_remove(V, ld, k, imv, mu2);
+      k = gram_remove<VS>(V, ld, k, imv, mu2);
       mask = mask_of(P, k);
     }
     if (capped) break;

@@ -40,6 +40,7 @@ struct PipeParams {
   const double *dbasis_cm;  // [nA][nT2][nTE]   d/d(alpha in degrees)
   const double *gram_set;   // [nA][nT2*ldg]     A_k'A_k per grid angle (Gram solver)
   int gram, ldg;            // solver variant (1 = normal-equation active set), leading dimension of G
+  int gv_stride;            // stride of the Gram solver's vectors in shared memory (gram.cuh: 40 or 64, >= nT2)
   int warps_per_cta, smem_per_warp;  // CTA shape: bytes of dynamic shared memory owned by each warp
   int fa_warm;              // warm-start flip-angle probes from a probed angle at most this many grid steps away (0 = never)
   int spill;                // which per-voxel tables live in global scratch instead of shared memory (SmemLayout)
@@ -81,13 +82,13 @@ struct SmemLayout {
   int M, c, y, s, t1, t2, lc_pts, lc_states, slots_x, fa_u, fa_du, fa_mask;  // Gram solver only
   // spill (Gram solver): bit 0 = the cached solutions (slots_x), bit 1 = the L-curve state records live in the warp's
   // global scratch instead (one L2 round trip per solve / per L-curve step, 2.5 KB each of shared memory back)
-  __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems, int gram, int spill = 0) {
+  __host__ __device__ SmemLayout(int nTE, int nT2, int rows_alloc, int a_elems, int gram, int spill = 0, int vs = 64) {
     int o = 0;
     b = u = M = c = y = s = t1 = t2 = lc_pts = lc_states = slots_x = fa_u = fa_du = fa_mask = 0;
     if (gram) {
       // solver block first (gram.cuh: vectors at fixed offsets from V, then the combined G / M array)
-      c = GV_C, y = GV_Y, s = GV_S, t1 = GV_T1, t2 = GV_T2, x = GV_X, w = GV_W, idx = GV_P;
-      A = GV_T, o = GV_T + a_elems;
+      c = 0, y = vs, s = 2 * vs, t1 = 3 * vs, t2 = 4 * vs, x = 5 * vs, w = 6 * vs, idx = 7 * vs;  // = GV_LAYOUT(vs)
+      A = gv_block_doubles(vs), o = A + a_elems;
       lc_pts = o, o += 4 * DECAES_LC_MAX;
       if (!(spill & 2)) lc_states = o, o += 5 * DECAES_LC_MAX;
       if (!(spill & 1)) slots_x = o, o += DECAES_NCACHE * nT2;
@@ -159,7 +160,7 @@ __constant__ PipeParams cP;
 #define VIEW_GWS() const GramWs gws = this->gws; SH(gws.y); SH(gws.s); SH(gws.x); SH(gws.w); SH(gws.t1); SH(gws.t2); SH(gws.P)
 
 // LEGACY instantiates the legacy = true searches (legacy.cuh); the default instantiation carries none of that code
-template <bool GRAM, bool LEGACY = false>
+template <bool GRAM, bool LEGACY = false, int VS = 64>
 struct Warp {
   long long prof_cyc[PF_COUNT] = {0};
   Src cursrc;
@@ -185,7 +186,7 @@ struct Warp {
 
   __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
       : sl(p.nTE, p.nT2, p.copy_elems, p.reg == 2) {
-    SmemLayout L(p.nTE, p.nT2, p.rows_alloc, p.a_elems, p.gram, p.spill);
+    SmemLayout L(p.nTE, p.nT2, p.rows_alloc, p.a_elems, p.gram, p.spill, p.gv_stride);
     ws.A = smem + L.A, ws.b = smem + L.b, ws.u = smem + L.u, ws.x = smem + L.x, ws.w = smem + L.w;
     ws.idx = (int *)(smem + L.idx);
     ws.ld = p.ld, ws.n = p.nT2, ws.m0 = p.nTE;
@@ -1228,7 +1229,7 @@ struct Warp {
       __syncwarp();
     }
     PROF_BEGIN(1);
-    o = gram_nnls(V, cP.nT2, cP.ldg, 0.0, max_set, warm_mask != 0ull, warm_mask);
+    o = gram_nnls<VS>(V, cP.nT2, cP.ldg, 0.0, max_set, warm_mask != 0ull, warm_mask);
 #ifdef DECAES_PROFILE
     if (lane == 0) {
       const int si = 28 + (nunreg_voxel < 19 ? nunreg_voxel : 19);
@@ -1462,7 +1463,7 @@ struct Warp {
       __syncwarp();
     }
     PROF_BEGIN(9);
-    o = gram_nnls(V, n, cP.ldg, mu2, n, nearest >= 0, nearest >= 0 ? slot_mask[nearest] : 0ull);
+    o = gram_nnls<VS>(V, n, cP.ldg, mu2, n, nearest >= 0, nearest >= 0 ? slot_mask[nearest] : 0ull);
 #ifdef DECAES_PROFILE
     if (lane == 0) {
       const int si = nsolve_voxel < 47 ? nsolve_voxel : 47;
