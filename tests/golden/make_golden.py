@@ -26,14 +26,21 @@ CASES = {
     "cfg4_gcv": (48, 8e-3, 60, "gcv", {}, {}),
     "cfg5_mdp": (32, 10e-3, 60, "mdp", {"NoiseLevel": 1e-3}, {"SPWin": (10e-3, 200e-3), "MPWin": (200e-3, 2.0)}),
     "refcon150_chi2": (32, 10e-3, 40, "chi2", {"Chi2Factor": 1.02, "RefConAngle": 150.0}, {}),
+    # legacy = true (src/types.jl:20-21, 59-63): 8 refocusing angles, all probed; sampled-spline flip angle and chi2 root
+    "legacy_chi2": (32, 10e-3, 40, "chi2", {"Chi2Factor": 1.02, "legacy": True, "nRefAngles": 8, "nRefAnglesMin": 8}, {}),
+    "legacy_none": (48, 8e-3, 40, "none", {"legacy": True, "nRefAngles": 8, "nRefAnglesMin": 8}, {}),
 }
+# seeds of the first seven cases are 100 + their rank in the sorted list of those seven names (kept as generated)
+_FIRST = sorted(["cfg1_none", "cfg2_lcurve48", "cfg3_lcurve56", "cfg4_chi2", "cfg4_gcv", "cfg5_mdp", "refcon150_chi2"])
+SEEDS = {n: 100 + i for i, n in enumerate(_FIRST)}
+SEEDS.update({"legacy_chi2": 121, "legacy_none": 122})
 NVOX = 64
 KEYS = ["dist", "gdn", "ggm", "gva", "fnr", "snr", "alpha", "mu", "chi2factor", "resnorm", "sfr", "sgm", "mfr", "mgm"]
 
 
 def compute(name):
     nTE, TE, nT2, Reg, extra, pextra = CASES[name]
-    seed = 100 + sorted(CASES).index(name)
+    seed = SEEDS[name]
     img = orc.mock_image(NVOX, nTE, TE, seed=seed)
     o = orc.make_t2map_opts((NVOX, 1, 1), nTE, nT2, TE, Reg=Reg, ngpus=1, **extra)
     p = orc.make_t2part_opts((NVOX, 1, 1), nT2, **pextra)
@@ -42,7 +49,7 @@ def compute(name):
 
 
 if __name__ == "__main__":
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         img, ref = compute(name)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), image=img, **ref)
         print(name, "written:", {k: v.shape for k, v in ref.items() if k in ("dist", "alpha")})
