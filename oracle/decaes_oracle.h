@@ -150,6 +150,7 @@ void orc_surrogate_search_legacy(orc_fg_fn fg, void *ctx, const double *grid, in
 
 /* ---------- legacy = true algorithms (oracle/orc_spline.c) ---------- */
 #define ORC_SPLINE_MAX 64
+#define ORC_CHI2_LEGACY_MAXPTS 22 /* mu = 0 plus at most 21 doublings of 1e-3; same cut as csrc/legacy.cuh */
 /* FITPACK curfit(iopt=0, s=0) + splev as wrapped by Dierckx.Spline1D (src/splines.jl:311-314) */
 int orc_fitpack_interp(const double *x, const double *y, int m, int k, double *t /* m+k+1 */, double *c /* m */);
 void orc_fitpack_splev(const double *t, int n, const double *c, int k, const double *x, int m, double *y);

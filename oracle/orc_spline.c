@@ -5,7 +5,7 @@
  *   CubicSplineSurrogate                        src/splines.jl:456-500
  *   chi2_search_from_minimum(...; legacy=true)  src/lsqnonneg.jl:595-636
  *
- * Third-party arithmetic: the interpolating spline is Dierckx.jl (Project.toml compat "0.5"), a
+ * Third-party arithmetic: the interpolating spline is Dierckx.jl (Project.toml:38, compat "0.4, 0.5"), a
  * wrapper of P. Dierckx's FITPACK (netlib ddierckx).  FITPACK is not under the reference checkout,
  * so its published algorithm is restated here routine by routine: curfit/fpcurf for iopt = 0,
  * s = 0 (knot placement of the interpolating spline, row-by-row Givens reduction of the
@@ -252,14 +252,14 @@ int orc_spline_root_legacy(const double *X, const double *Y, int m, double value
 /* chi2_search_from_minimum(f, res2min, chi2fact; legacy = true)  src/lsqnonneg.jl:595-636:
  * mu doubles from 1e-3 until res2(mu) >= chi2fact * res2min, then the sampled spline root through
  * every (mu, res2) seen, mu = 0 included.  Returns 0, or -1 when the doubling does not terminate
- * within ORC_SPLINE_MAX - 1 steps (the reference would loop on). */
+ * within ORC_CHI2_LEGACY_MAXPTS - 1 = 21 steps (mu ~ 1049; the reference would loop on; the GPU uses the same cut). */
 int orc_chi2_search_legacy(orc_fn1 f, void *ctx, double res2min, double chi2fact, double *mu_out, double *res2_out) {
-  double mus[ORC_SPLINE_MAX], rs[ORC_SPLINE_MAX];
+  double mus[ORC_CHI2_LEGACY_MAXPTS], rs[ORC_CHI2_LEGACY_MAXPTS];
   int n = 0;
   mus[n] = 0.0, rs[n] = res2min, n++;
   double munew = 1e-3;
   while (1) {
-    if (n >= ORC_SPLINE_MAX) return -1;
+    if (n >= ORC_CHI2_LEGACY_MAXPTS) return -1;
     double r = f(munew, ctx);
     mus[n] = munew, rs[n] = r, n++;
     if (r >= chi2fact * res2min) break;
