@@ -124,6 +124,14 @@ function t2part_gpu(T2distributions::Array{Float64, 4}, opts::T2partOptions{Floa
     return convert(Dict{String, Any}, maps)
 end
 
+"""
+    release()
+
+Give back the device workspaces the library keeps between calls (`decaes_release`): basis tables, per-warp
+scratch and the device copy of each GPU's voxel slab.
+"""
+release() = ccall((:decaes_release, libdecaes_cuda), Cvoid, ())
+
 # Route the public Float64 entry points through the GPU library (the two-line patch a maintainer
 # would apply inside DECAES itself is shown in INTEGRATION.md).
 # `legacy = true` (sampled FITPACK spline for the flip angle and for the chi2 root, src/splines.jl:419-446,

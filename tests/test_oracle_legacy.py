@@ -138,3 +138,41 @@ def test_legacy_pipeline(Reg, extra):
         ok = mu > 0
         assert ok.mean() > 0.5
         assert np.all(res["chi2factor"][ok] > 1.0) and np.median(res["chi2factor"][ok]) < 1.2
+
+
+def test_four_points_make_the_spline_an_exact_surrogate_of_a_cubic():
+    """test/splines.jl:123-163 (test_cubic_spline_surrogate) for the legacy suggest_point: with four points the
+    FITPACK spline is the cubic itself, so the sampled minimum sits within half a grid step of the analytic one."""
+    x = np.linspace(-0.5, 2.0, 4)
+    f = lambda t: 3 * t ** 3 - 5 * t ** 2 - t - 2  # noqa: E731
+    u = f(x)
+    xs, us, order = orc.surrogate_search(lambda I: (u[I - 1], 0.0), x, 4, 4, legacy=True)
+    assert sorted(order) == [1, 2, 3, 4]
+    xtrue = (10 + np.sqrt(100 + 36)) / 18  # root of 9x^2 - 10x - 1 inside the interval, a minimum (f'' > 0)
+    assert abs(xs - xtrue) <= 0.0005 + 1e-12
+    assert abs(us - f(xs)) <= 1e-12 and us <= f(xtrue) + 9 * 0.0005 ** 2  # f'' = 18x - 10 < 18 around xtrue
+    t, c = orc.fitpack_interp(x, u, 3)
+    grid = np.linspace(-0.5, 2.0, 1001)
+    assert np.allclose(orc.fitpack_splev(t, c, 3, grid), f(grid), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("npts,deg", [(n, d) for n in range(2, 6) for d in range(1, min(n - 1, 3) + 1)])
+def test_cubic_splines_minimum_and_root(npts, deg):
+    """test/splines.jl:100-121 (test_cubic_splines) restated for the sampled legacy searches; the legacy functions
+    always take deg_spline = min(3, npts - 1) (src/splines.jl:419, 446), so only that degree applies."""
+    if deg != min(3, npts - 1):
+        pytest.skip("legacy searches use deg_spline = min(3, npts - 1)")
+    rng = np.random.default_rng(10 * npts + deg)
+    X = np.linspace(-0.5, 2.0, npts)
+    Y = rng.standard_normal(npts)
+    t, c = orc.fitpack_interp(X, Y, deg)
+    x, y = orc.spline_opt_legacy(X, Y)
+    assert X[0] <= x <= X[-1]
+    assert abs(orc.fitpack_splev(t, c, deg, [x])[0] - y) <= 1e-14 * max(1.0, abs(y))
+    dense = orc.fitpack_splev(t, c, deg, np.linspace(X[0], X[-1], 100))
+    assert dense.min() >= y - 5e-3  # 100 points against 2501 samples: the sampled minimum can only be lower, up to slope * step
+    ybar = (Y.min() + Y.max()) / 2
+    xbar = orc.spline_root_legacy(X, Y, ybar)
+    assert X[0] <= xbar <= X[-1]
+    slope = np.abs(np.diff(orc.fitpack_splev(t, c, deg, np.linspace(X[0], X[-1], 2501)))).max() / 0.001
+    assert abs(orc.fitpack_splev(t, c, deg, [xbar])[0] - ybar) <= slope * 0.0005 + 1e-9
