@@ -54,6 +54,9 @@ class RunStats(C.Structure):
         ("ngpus_used", C.c_int32), ("kernel_launches", C.c_int32),
         ("setup_ms", C.c_double), ("pipeline_ms", C.c_double),
         ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
+        # ABI v2 (appended): counted voxels, see include/decaes_cuda.h
+        ("early_returns", C.c_int64), ("lcurve_overflow", C.c_int64), ("nnls_itercap", C.c_int64),
+        ("pinned_staging", C.c_int64),
     ]
 
 

@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
     if (processed) atomicAdd(&P.counters[1], processed);
     if (W.n_early) atomicAdd(&P.counters[2], W.n_early);
     if (W.n_overflow) atomicAdd(&P.counters[3], W.n_overflow);
+    if (W.n_itercap) atomicAdd(&P.counters[26], W.n_itercap);
   }
 }
 
@@ -621,12 +622,17 @@ struct DeviceWs {
   cudaDeviceProp prop;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_pending = false;
+  bool ev2_recorded = false;  // ev[2] marks the end of the last pipeline kernel enqueued on this device (any stream)
   int chunks_pending = 0;  // pipeline launches since the last collect_device_stats (one counter block each)
   int sm_count = 0;
 };
 #define DECAES_MAX_CHUNKS 8  // sub-slabs of one device's slab whose copies overlap the neighbours' kernels
 static std::mutex g_ws_mutex;
 static DeviceWs g_ws[64];
+// One set of tables / scratch / counters / kernel parameters (the __constant__ cP) exists per device, so everything
+// that plans or launches on a device holds that device's mutex, and a new launch waits for the previous pipeline
+// kernel of the device on the GPU side too (launch_pipeline: cudaStreamWaitEvent on ev[2]).
+static std::recursive_mutex g_dev_mutex[64];
 
 static int ensure(double **p, size_t *cap, size_t need_doubles) {
   if (*cap >= need_doubles) return DECAES_OK;
@@ -712,6 +718,11 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     int rc = make_part_tables(part, &pt);
     if (rc) return rc;
     if (part->nT2 != nT2) return fail(DECAES_EINVAL, "T2part nT2 (%d) != T2map nT2 (%d)", part->nT2, nT2);
+    // the fused epilogue shares the T2 grid of the map (log T2 table, window indices): a different T2Range would
+    // silently disagree with the standalone T2partSEcorr on the same distribution
+    if (part->T2min != o->T2min || part->T2max != o->T2max)
+      return fail(DECAES_EINVAL, "fused T2part needs the T2Range of the T2map options ((%g, %g) != (%g, %g)); call decaes_t2part on the distribution instead",
+                  part->T2min, part->T2max, o->T2min, o->T2max);
     P.has_part = 1, P.sp_lo = pt.sp_lo, P.sp_hi = pt.sp_hi, P.mp_lo = pt.mp_lo, P.mp_hi = pt.mp_hi;
     P.has_sigmoid = pt.has_sigmoid;
     memcpy(P.weights, pt.weights, sizeof pt.weights);
@@ -825,6 +836,9 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
   P.decaybasis = o->decaybasis;
   P.sfr = o->sfr, P.sgm = o->sgm, P.mfr = o->mfr, P.mgm = o->mgm;
   DeviceWs &ws = g_ws[dev];
+  // the previous launch on this device may still be running on another stream: it owns cP, the scratch and (chunk 0)
+  // the basis tables until its kernel has finished
+  if (ws.ev2_recorded) CUDA_TRY(cudaStreamWaitEvent(stream, ws.ev[2], 0));
   P.counters = ws.counters + 32 * chunk;
   CUDA_TRY(cudaMemsetAsync(P.counters, 0, 32 * sizeof(unsigned long long), stream));
   if (chunk == 0) {  // the per-run tables are shared by every chunk of the slab
@@ -869,6 +883,7 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
   }
   CUDA_TRY(cudaEventRecord(ws.ev[2], stream));  // re-recorded by every chunk: ev[1] -> ev[2] spans all of them
   ws.ev_pending = true;
+  ws.ev2_recorded = true;
   ws.chunks_pending = chunk + 1;
   return DECAES_OK;
 }
@@ -888,6 +903,7 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
   st->setup_ms = std::max(st->setup_ms, (double)a);
   st->pipeline_ms = std::max(st->pipeline_ms, (double)b);
   st->voxels_processed += (int64_t)c[1];
+  st->early_returns += (int64_t)c[2], st->lcurve_overflow += (int64_t)c[3], st->nnls_itercap += (int64_t)c[26];
   if (getenv("DECAES_PHASE_CYCLES"))
     fprintf(stderr, "[decaes] warp-cycles per voxel: barrier %.0f  flip-angle %.0f  basis %.0f  solve+save %.0f  total %.0f\n",
             (double)c[4] / std::max<double>(1.0, (double)c[1]), (double)c[5] / std::max<double>(1.0, (double)c[1]),
@@ -955,9 +971,12 @@ int decaes_device_count(void) {
 void decaes_get_stats(decaes_run_stats *stats) {
   // device-API calls leave their events pending; resolve them now
   int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && g_ws[dev].ev_pending) {
-    g_stats.ngpus_used = 1;
-    collect_device_stats(dev, &g_stats);
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+    std::lock_guard<std::recursive_mutex> dl(g_dev_mutex[dev]);
+    if (g_ws[dev].ev_pending) {
+      g_stats.ngpus_used = 1;
+      collect_device_stats(dev, &g_stats);
+    }
   }
   if (stats) *stats = g_stats;
 }
@@ -971,6 +990,8 @@ int decaes_t2map_device(const double *d_image, int64_t nvox, int64_t stride, con
   if (!d_image || nvox < 0 || stride < nvox) return fail(DECAES_EINVAL, "bad image pointer / nvox / stride");
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(DECAES_EUNSUPPORTED, "device index %d out of range", dev);
+  std::lock_guard<std::recursive_mutex> dl(g_dev_mutex[dev]);
   Plan plan;
   if ((rc = make_plan(opts, part, dev, &plan))) return rc;
   memset(&g_stats, 0, sizeof g_stats);
@@ -1061,8 +1082,11 @@ int decaes_setup_tables(const decaes_t2map_opts *o, double *echotimes, double *t
   if (decaybasisset) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(DECAES_EUNSUPPORTED, "device index %d out of range", dev);
+    std::lock_guard<std::recursive_mutex> dl(g_dev_mutex[dev]);
     Plan plan;
     if ((rc = make_plan(o, nullptr, dev, &plan))) return rc;
+    if (g_ws[dev].ev2_recorded) CUDA_TRY(cudaEventSynchronize(g_ws[dev].ev[2]));  // a running pipeline reads these tables
     basis_setup_kernel<<<(nA * nT2 + 63) / 64, 64>>>(plan.S);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(decaybasisset, plan.S.basis_cm, sizeof(double) * (size_t)nA * nTE * nT2, cudaMemcpyDeviceToHost));
@@ -1084,6 +1108,8 @@ struct SlabJob {
 static int run_slab(SlabJob &job, const double *image, int64_t Nvox, const decaes_t2map_opts *opts,
                     const decaes_t2part_opts *part, const decaes_t2map_out *out) {
   CUDA_TRY(cudaSetDevice(job.dev));
+  if (job.dev < 0 || job.dev >= 64) return fail(DECAES_EUNSUPPORTED, "device index %d out of range", job.dev);
+  std::lock_guard<std::recursive_mutex> dl(g_dev_mutex[job.dev]);
   const int nTE = opts->nTE, nT2 = opts->nT2;
   const int64_t nv = job.v1 - job.v0;
   memset(&job.st, 0, sizeof job.st);
@@ -1240,6 +1266,8 @@ int decaes_t2map(const double *image, const decaes_t2map_opts *opts, const decae
   for (auto &j : jobs) {
     if (j.rc) return fail(j.rc, "device %d: %s", j.dev, j.err);
     g_stats.voxels_processed += j.st.voxels_processed;
+    g_stats.early_returns += j.st.early_returns, g_stats.lcurve_overflow += j.st.lcurve_overflow;
+    g_stats.nnls_itercap += j.st.nnls_itercap, g_stats.pinned_staging |= j.st.pinned_staging;
     g_stats.kernel_launches += j.st.kernel_launches;
     g_stats.setup_ms = std::max(g_stats.setup_ms, j.st.setup_ms);
     g_stats.pipeline_ms = std::max(g_stats.pipeline_ms, j.st.pipeline_ms);

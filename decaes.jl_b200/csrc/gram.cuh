@@ -63,6 +63,7 @@ struct GramOut {
   unsigned long long mask;   // active set as a bit mask
   double xnorm_sq;           // sum of squares of the solution
   int iters, nappend;        // diagnostics (DECAES_PROFILE histograms)
+  bool capped;               // stopped by the 3n iteration cap (mode = 1, src/NNLS.jl:693-698)
 };
 
 #define GM_(t, u) T[(u) * ld + (t) + 1]
@@ -359,6 +360,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
   GP_BEGIN();
   GP_ADD(warm ? 11 : 12, 1);
   int k = 0, iter = 0, nappend = 0;
+  bool hit_cap = false;
   const int max_iter = 3 * n;
   bool check_first = false;
   // the two columns of this lane (n <= 64); out-of-range ones are clamped and never win
@@ -457,7 +459,10 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
       k = gram_remove<VS>(V, ld, k, imv, mu2);
       mask = mask_of(P, k);
     }
-    if (capped) break;
+    if (capped) {
+      hit_cap = true;
+      break;
+    }
 
     _Pragma("unroll 1") for (int t = lane; t < k; t += 32) V[GV_X + P[t]] = V[GV_S + t];
     __syncwarp();
@@ -491,7 +496,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
   double acc = 0.0;
   _Pragma("unroll 1") for (int j = lane; j < n; j += 32) acc = fma(V[GV_X + j], V[GV_X + j], acc);
   o.xnorm_sq = warp_sum(acc);
-  o.iters = iter, o.nappend = nappend;
+  o.iters = iter, o.nappend = nappend, o.capped = hit_cap;
   GP_ADD(13, k);
   GP_ADD(14, iter);
   GP_END(3);

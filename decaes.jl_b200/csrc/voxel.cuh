@@ -54,7 +54,7 @@ struct PipeParams {
   // scratch + scheduling
   double *scratch;          // per-warp global scratch
   long long scratch_per_warp;
-  unsigned long long *counters;  // [0] work counter, [1] voxels processed, [2] early returns, [3] lcurve overflow
+  unsigned long long *counters;  // [0] work counter, [1] voxels processed, [2] early returns, [3] lcurve overflow, [26] NNLS iteration caps
 };
 
 // layout of the per-warp global scratch (in doubles)
@@ -181,7 +181,7 @@ struct Warp {
   int dirty_rows;   // lambda rows of the working matrix that may be non-zero
   int cur_slot;     // 0-based current cache slot (persists across voxels like work.idx[])
   int lane;
-  unsigned long long n_early, n_overflow;
+  unsigned long long n_early, n_overflow, n_itercap;
   int nsolve_voxel = 0, nunreg_voxel = 0;  // Tikhonov / unregularised solves of the current voxel (DECAES_PROFILE)
 
   __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
@@ -211,7 +211,7 @@ struct Warp {
     dirty_rows = p.rows_alloc - p.nTE;
     cur_slot = 0;
     lane = lane_id();
-    n_early = n_overflow = 0;
+    n_early = n_overflow = n_itercap = 0;
   }
 
   // ---- TMA: stage one nTE x nT2 matrix (row-major, ld) from global into the working matrix ----
@@ -1230,6 +1230,7 @@ struct Warp {
     }
     PROF_BEGIN(1);
     o = gram_nnls<VS>(V, cP.nT2, cP.ldg, 0.0, max_set, warm_mask != 0ull, warm_mask);
+    n_itercap += o.capped;
 #ifdef DECAES_PROFILE
     if (lane == 0) {
       const int si = 28 + (nunreg_voxel < 19 ? nunreg_voxel : 19);
@@ -1464,6 +1465,7 @@ struct Warp {
     }
     PROF_BEGIN(9);
     o = gram_nnls<VS>(V, n, cP.ldg, mu2, n, nearest >= 0, nearest >= 0 ? slot_mask[nearest] : 0ull);
+    n_itercap += o.capped;
 #ifdef DECAES_PROFILE
     if (lane == 0) {
       const int si = nsolve_voxel < 47 ? nsolve_voxel : 47;

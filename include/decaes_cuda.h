@@ -26,6 +26,10 @@
  *     `alpha` keeps the caller's value there when alpha_provided = 1.
  *   - *_device entry points take DEVICE pointers on the current CUDA device and enqueue
  *     on the given stream (cudaStream_t passed as void*); they do not synchronise.
+ *     The library keeps ONE set of per-device tables, scratch and kernel parameters, so
+ *     launches on the same device are serialised: a per-device mutex guards the host side and
+ *     every new launch waits (cudaStreamWaitEvent) for the previous pipeline kernel of that
+ *     device, whatever stream it was enqueued on.  Different devices run concurrently.
  *   - Return value: 0 on success, negative decaes_status on failure; the message is in
  *     decaes_last_error() (thread-local).  Nothing throws across the ABI.
  *   - There is no CPU fallback: without a usable CUDA device every compute entry point
@@ -40,7 +44,7 @@
 extern "C" {
 #endif
 
-#define DECAES_ABI_VERSION 1
+#define DECAES_ABI_VERSION 2  /* v2: decaes_run_stats grew the counted-voxel fields (appended; v1 prefix unchanged) */
 
 typedef enum {
   DECAES_OK = 0,
@@ -114,6 +118,17 @@ typedef struct {
   double pipeline_ms;       /* voxel pipeline kernel (device time, max)         */
   double h2d_ms, d2h_ms;    /* host API only                                    */
   double total_ms;          /* host wall time of the call                       */
+  /* ---- ABI v2: voxels the north_star wants "counted and reported" ---- */
+  int64_t early_returns;    /* voxels that took an early-return branch of lsqnonneg_chi2!/lsqnonneg_mdp!
+                               (src/lsqnonneg.jl:510-515, 708-718): the reference's save_results! reads a stale
+                               cache slot there (reference-undefined); this library returns the chooser's own
+                               result.  Legacy chi2 searches that ended at mu = 0 / did not end are counted too. */
+  int64_t lcurve_overflow;  /* L-curve searches that outgrew the per-voxel point / state cache (the reference's
+                               GrowableCache, src/utils.jl:140-254, grows without bound); 0 on every benchmark
+                               configuration — a non-zero value means the result of that voxel is approximate. */
+  int64_t nnls_itercap;     /* NNLS solves stopped by the 3n iteration cap (mode = 1, src/NNLS.jl:693-698)      */
+  int64_t pinned_staging;   /* host API: 1 when pageable caller buffers were staged through the library's pinned
+                               ring (0: the caller's buffers were already page-locked and used directly)       */
 } decaes_run_stats;
 
 /* ---- host-pointer API (what the Julia shim ccalls) ---- */

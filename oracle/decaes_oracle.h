@@ -26,6 +26,22 @@
 
 #include <stddef.h>
 #include <stdint.h>
+
+/* Two builds of the same sources (oracle/Makefile):
+ *   liborc.so       the CHECKER: reductions in plain sequential order (ORC_SIMD undefined).
+ *   liborc_simd.so  -DORC_SIMD: the loops that carry @simd in the reference (src/NNLS.jl:278-462, 813, 1049;
+ *                   src/lsqnonneg.jl:46-64, 117-139) are vectorised with reassociated partial sums, which is
+ *                   what LLVM does to them in Julia.  It is (a) the CPU baseline that bench.py times and
+ *                   (b) the "second faithful CPU build" against which the L-curve mu-flip rate of the GPU is
+ *                   judged (tools/lcurve_ab.py): two builds of the same algorithm that differ only in the
+ *                   summation order of those loops already choose a different mu for a few percent of voxels. */
+#define ORC_STR_(x) #x
+#define ORC_STR(x) ORC_STR_(x)
+#ifdef ORC_SIMD
+#define ORC_SIMD_REDUCE(v) _Pragma(ORC_STR(omp simd reduction(+ : v)))
+#else
+#define ORC_SIMD_REDUCE(v)
+#endif
 #include "../include/decaes_cuda.h"
 
 #ifdef __cplusplus

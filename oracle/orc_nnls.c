@@ -67,6 +67,7 @@ static double construct_apply_householder(double *A, int lda, double *b, int ip,
   if (ip > m) return 0.0;
   double alpha = A_(ip, jp);
   double xnorm = 0.0;
+  ORC_SIMD_REDUCE(xnorm) /* @simd, src/NNLS.jl:278 */
   for (int i = ip; i <= m; i++) xnorm = fma(A_(i, jp), A_(i, jp), xnorm);
   xnorm = sqrt(xnorm);
   if (xnorm == 0.0) return -1.0;
@@ -76,6 +77,7 @@ static double construct_apply_householder(double *A, int lda, double *b, int ip,
   double tau = alpha / beta;
 
   double sm = B_(ip);
+  ORC_SIMD_REDUCE(sm) /* @simd, src/NNLS.jl:292 */
   for (int i = ip + 1; i <= m; i++) sm = fma(B_(i), A_(i, jp) / alpha, sm);
   sm *= -tau;
 
@@ -132,10 +134,12 @@ static void apply_householder_dual(double *A, int lda, int n, double *w, const d
   A_(j1, j1) = 1.0;
   for (int j = j1 + 1; j <= n; j++) {
     double sm = 0.0;
+    ORC_SIMD_REDUCE(sm) /* @simd, src/NNLS.jl:398, 418 */
     for (int i = j1; i <= m1; i++) sm = fma(A_(i, j), A_(i, j1), sm);
     sm *= -tau;
     double wj = 0.0;
     A_(j1, j) = A_(j1, j) + sm;
+    ORC_SIMD_REDUCE(wj) /* @simd, src/NNLS.jl:405, 424 */
     for (int i = j1 + 1; i <= m1; i++) {
       double Aij = fma(sm, A_(i, j1), A_(i, j));
       wj = fma(Aij, B_(i), wj);
@@ -150,6 +154,7 @@ static void apply_householder_dual(double *A, int lda, int n, double *w, const d
 static void compute_dual(double *w, const double *A, int lda, int n, const double *b, int j1, int m1) {
   for (int j = j1; j <= n; j++) {
     double sm = 0.0;
+    ORC_SIMD_REDUCE(sm) /* @simd, src/NNLS.jl:452, 462 */
     for (int i = j1; i <= m1; i++) sm = fma(A_(i, j), B_(i), sm);
     W_(j) = sm;
   }
@@ -342,6 +347,7 @@ static void unsafe_nnls(orc_nnls_work *wk, int Mrows, int mrows, int init_dual, 
   const int mres = tikh ? M : m;
   double sm = 0.0;
   if (nsetp < mres) {
+    ORC_SIMD_REDUCE(sm) /* @simd, src/NNLS.jl:813, 1049 */
     for (int i = nsetp + 1; i <= mres; i++) {
       double bi = B_(i);
       ZZ_(i) = bi;
@@ -387,13 +393,16 @@ static void warm_start(orc_nnls_work *wk, const double *A0, int lda0, const doub
 #define A0_(i, j) A0[((size_t)(i)-1) + ((size_t)(j)-1) * (size_t)lda0]
 #define C_(i, j) C[((size_t)(i)-1) + ((size_t)(j)-1) * (size_t)ldc]
   double den = 0.0;
+  ORC_SIMD_REDUCE(den) /* @simd, src/lsqnonneg.jl:46, 117 */
   for (int i = 1; i <= m; i++) den = fma(A0_(i, n), A0_(i, n), den);
   if (tikh) den += mu * mu;
   double xj = 0.0;
+  ORC_SIMD_REDUCE(xj) /* @simd, src/lsqnonneg.jl:51, 123 */
   for (int i = 1; i <= m; i++) xj = fma(A0_(i, n) / den, b0[i - 1], xj);
   for (int i = 1; i <= m; i++) z[i - 1] = b0[i - 1] - A0_(i, n) * xj;
   for (int j = 1; j <= n - 1; j++) {
     double wj = 0.0;
+    ORC_SIMD_REDUCE(wj) /* @simd, src/lsqnonneg.jl:62, 134 */
     for (int i = 1; i <= m; i++) {
       double Aij = A0_(i, j);
       wj = fma(Aij, z[i - 1], wj);

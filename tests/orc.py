@@ -472,14 +472,42 @@ def alloc_outputs(nvox, nTE, nT2, part=True, save_reg=True, save_resnorm=True, s
     return arrs, out
 
 
-def t2map(image, opts, part=None, nthreads=0, **alloc_kw):
+_variants = {}
+
+
+def lib_variant(name):
+    """Another build of the same oracle sources (oracle/Makefile): "simd" (liborc_simd.so: the reference's @simd
+    reductions vectorised / reassociated) or "native" (the same with -march=native, built on this machine if gcc is
+    here; falls back to "simd").  Only orc_t2map is declared: these builds are timed / compared, never the checker."""
+    if name in _variants:
+        return _variants[name]
+    build()
+    path = os.path.join(ORACLE_DIR, "_build", f"liborc_{name}.so")
+    if name == "native":
+        try:
+            subprocess.run(["make", "-C", ORACLE_DIR, "native"], check=True, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL)
+        except Exception:
+            pass
+        if not os.path.exists(path):
+            return lib_variant("simd")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", ORACLE_DIR], check=True, stdout=subprocess.DEVNULL)
+    L = C.CDLL(path)
+    L.orc_t2map.argtypes = lib().orc_t2map.argtypes
+    L._decaes_variant = os.path.basename(path)
+    _variants[name] = L
+    return L
+
+
+def t2map(image, opts, part=None, nthreads=0, L=None, **alloc_kw):
     """image: (nvox, nTE) array-like in Julia memory order, i.e. image.T.ravel() is [echo][voxel]."""
     img = np.asfortranarray(image, dtype=np.float64)  # (nvox, nTE) column-major -> v + e*nvox
     nvox, nTE = img.shape
     arrs, out = alloc_outputs(nvox, nTE, opts.nT2, part=part is not None, **alloc_kw)
     st = Stats()
-    rc = lib().orc_t2map(img.ctypes.data_as(dp), nvox, nvox, C.byref(opts), C.byref(part) if part is not None else None,
-                         C.byref(out), nthreads, C.byref(st))
+    rc = (L or lib()).orc_t2map(img.ctypes.data_as(dp), nvox, nvox, C.byref(opts), C.byref(part) if part is not None else None,
+                                C.byref(out), nthreads, C.byref(st))
     if rc != 0:
         raise ValueError(f"orc_t2map failed with status {rc}")
     arrs["dist"] = arrs["dist"].reshape(opts.nT2, nvox).T

@@ -30,7 +30,7 @@ def test_header_symbols_are_exported(pkg):
     assert declared == set(pkg._abi.DECLARED_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.decaes_abi_version() == 1
+    assert L.decaes_abi_version() == 2
 
 
 def test_struct_layouts_match_header(pkg):
@@ -42,6 +42,7 @@ def test_struct_layouts_match_header(pkg):
       printf("%zu %zu %zu %zu\n", sizeof(decaes_t2map_opts), sizeof(decaes_t2part_opts), sizeof(decaes_t2map_out), sizeof(decaes_run_stats));
       printf("%zu %zu %zu\n", offsetof(decaes_t2map_opts, TE), offsetof(decaes_t2map_opts, SetFlipAngle), offsetof(decaes_t2part_opts, Sigmoid));
       printf("%zu %zu\n", offsetof(decaes_t2map_out, dist), offsetof(decaes_run_stats, total_ms));
+      printf("%zu %zu\n", offsetof(decaes_run_stats, early_returns), offsetof(decaes_run_stats, pinned_staging));
       return 0;
     }"""
     with tempfile.TemporaryDirectory() as d:
@@ -52,7 +53,8 @@ def test_struct_layouts_match_header(pkg):
     a = pkg._abi
     got = [C.sizeof(a.T2mapOpts), C.sizeof(a.T2partOpts), C.sizeof(a.T2mapOut), C.sizeof(a.RunStats),
            a.T2mapOpts.TE.offset, a.T2mapOpts.SetFlipAngle.offset, a.T2partOpts.Sigmoid.offset,
-           a.T2mapOut.dist.offset, a.RunStats.total_ms.offset]
+           a.T2mapOut.dist.offset, a.RunStats.total_ms.offset, a.RunStats.early_returns.offset,
+           a.RunStats.pinned_staging.offset]
     assert got == [int(x) for x in out]
 
 
