@@ -52,6 +52,12 @@ def lib():
         dp, vp = C.POINTER(C.c_double), C.c_void_p
         L.decaes_last_error.restype = C.c_char_p
         L.decaes_t2map.argtypes = [vp, C.POINTER(T2mapOpts), C.POINTER(T2partOpts), C.POINTER(T2mapOut)]
+        L.decaes_t2map_f32.argtypes = [vp, C.POINTER(T2mapOpts), C.POINTER(T2partOpts), C.POINTER(T2mapOut)]
+        L.decaes_host_alloc.restype = vp
+        L.decaes_host_alloc.argtypes = [C.c_size_t]
+        L.decaes_host_free.restype = None
+        L.decaes_host_free.argtypes = [vp]
+        L.decaes_slab_bounds_masked.argtypes = [vp, C.c_int64, C.c_double, C.c_int32, C.POINTER(C.c_int64)]
         L.decaes_t2part.argtypes = [vp, C.POINTER(T2partOpts), vp, vp, vp, vp]
         L.decaes_setup_tables.argtypes = [C.POINTER(T2mapOpts), vp, vp, vp, vp]
         L.decaes_t2map_device.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(T2mapOpts), C.POINTER(T2partOpts),
@@ -238,7 +244,9 @@ def T2mapSEcorr(image, opts: Optional[T2mapOptions] = None, B1map=None, t2part: 
         raise TypeError("pass either an options struct or keyword arguments")
     if tuple(image.shape) != (*opts.MatrixSize, opts.nTE):
         raise AssertionError(f"size(image) == (opts.MatrixSize..., opts.nTE) failed: {image.shape}")
-    img = np.asfortranarray(image, dtype=np.float64)
+    # Float32 volumes go to the library as they are (converted on the device, decaes_t2map_f32)
+    is_f32 = image.dtype == np.float32
+    img = np.asfortranarray(image, dtype=np.float32 if is_f32 else np.float64)
     L = lib()
     msz, nTE, nT2 = opts.MatrixSize, opts.nTE, opts.nT2
     fixed = opts.SetFlipAngle is not None
@@ -282,7 +290,8 @@ def T2mapSEcorr(image, opts: Optional[T2mapOptions] = None, B1map=None, t2part: 
         if name == "decaybasis" and fixed:
             arr = None
         setattr(out, name, _ptr(arr))
-    _check(L.decaes_t2map(_ptr(img), C.byref(copts), C.byref(cpart) if cpart is not None else None, C.byref(out)))
+    entry = L.decaes_t2map_f32 if is_f32 else L.decaes_t2map
+    _check(entry(_ptr(img), C.byref(copts), C.byref(cpart) if cpart is not None else None, C.byref(out)))
     return maps, dist
 
 
@@ -332,6 +341,14 @@ def slab_bounds(nvox, nshards, index):
     v0, v1 = C.c_int64(), C.c_int64()
     _check(lib().decaes_slab_bounds(nvox, nshards, index, C.byref(v0), C.byref(v1)))
     return v0.value, v1.value
+
+
+def slab_bounds_masked(first_echo, threshold, nshards):
+    """Cuts of decaes_slab_bounds_masked: equal numbers of voxels above `threshold` per shard."""
+    fe = np.ascontiguousarray(first_echo, dtype=np.float64).ravel()
+    cuts = (C.c_int64 * (nshards + 1))()
+    _check(lib().decaes_slab_bounds_masked(fe.ctypes.data, fe.size, float(threshold), nshards, cuts))
+    return list(cuts)
 
 
 def measure_fp64_peak():

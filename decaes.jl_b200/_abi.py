@@ -65,5 +65,5 @@ DECLARED_SYMBOLS = [
     "decaes_t2map", "decaes_t2part", "decaes_setup_tables", "decaes_t2map_device",
     "decaes_t2part_device", "decaes_mock_image_device", "decaes_last_error",
     "decaes_device_count", "decaes_abi_version", "decaes_get_stats", "decaes_measure_fp64_peak",
-    "decaes_slab_bounds", "decaes_release",
+    "decaes_slab_bounds", "decaes_release", "decaes_t2map_f32", "decaes_host_alloc", "decaes_host_free", "decaes_slab_bounds_masked",
 ]

@@ -625,7 +625,11 @@ struct DeviceWs {
   bool ev2_recorded = false;  // ev[2] marks the end of the last pipeline kernel enqueued on this device (any stream)
   int chunks_pending = 0;  // pipeline launches since the last collect_device_stats (one counter block each)
   int sm_count = 0;
+  void *ring[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned staging ring (host API, pageable caller buffers)
+  cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t ring_cap = 0;  // bytes per slot
 };
+#define DECAES_NSTAGE 4
 #define DECAES_MAX_CHUNKS 8  // sub-slabs of one device's slab whose copies overlap the neighbours' kernels
 static std::mutex g_ws_mutex;
 static DeviceWs g_ws[64];
@@ -1105,7 +1109,53 @@ struct SlabJob {
   decaes_run_stats st;
 };
 
-static int run_slab(SlabJob &job, const double *image, int64_t Nvox, const decaes_t2map_opts *opts,
+// Float32 volume -> the Float64 image the pipeline reads (copyto!(Array{Float64,4}(undef, sz), data), src/main.jl:612-617,
+// done on the device: the conversion is exact and the host-to-device traffic halves)
+__global__ void f32_to_f64_kernel(const float *__restrict__ src, double *__restrict__ dst, long long n, long long pitch, int rows) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  for (int r = 0; r < rows; r++) dst[v + r * pitch] = (double)src[v + r * pitch];
+}
+
+// Pinned staging ring of one device (host API, pageable caller buffers): DECAES_NSTAGE slots that alternate between
+// "being filled by the host / drained by the device" (H2D) and "being filled by the device / drained by the host" (D2H).
+static int ring_ensure(DeviceWs &ws, size_t bytes) {
+  if (ws.ring_cap >= bytes) return DECAES_OK;
+  for (int s = 0; s < DECAES_NSTAGE; s++) {
+    if (ws.ring[s]) cudaFreeHost(ws.ring[s]);
+    ws.ring[s] = nullptr;
+  }
+  ws.ring_cap = 0;
+  for (int s = 0; s < DECAES_NSTAGE; s++) {
+    if (cudaHostAlloc(&ws.ring[s], bytes, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(DECAES_ENOMEM, "cannot allocate %zu bytes of pinned staging memory", bytes);
+    }
+    if (!ws.ring_ev[s]) CUDA_TRY(cudaEventCreateWithFlags(&ws.ring_ev[s], cudaEventDisableTiming));
+  }
+  ws.ring_cap = bytes;
+  return DECAES_OK;
+}
+
+static bool host_ptr_is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// One device's share of a host-API call: voxels [job.v0, job.v1) of the caller's arrays.
+//   * the device copy of the slab (image + every requested output) is one cached allocation;
+//   * the slab is processed as sub-slabs ("chunks") so that transfers overlap the neighbouring chunks' kernels;
+//   * page-locked caller buffers are copied directly (cudaMemcpy2DAsync, strided by Nvox); pageable ones - what Julia
+//     hands over (src/T2mapSEcorr.jl:24-54 allocates ordinary Arrays) - go through the device's pinned staging ring:
+//     the host thread packs rows into a slot, the copy engine moves the slot, and results come back the same way, so
+//     the copies stay asynchronous and at full PCIe rate (a cudaMemcpy from pageable memory would block the host and
+//     run at a fraction of it).  cudaHostRegister on the caller's buffers was ruled out: pinning 5.5 GB costs more
+//     than the whole 8-GPU run.
+static int run_slab(SlabJob &job, const void *image_any, bool img_f32, int64_t Nvox, const decaes_t2map_opts *opts,
                     const decaes_t2part_opts *part, const decaes_t2map_out *out) {
   CUDA_TRY(cudaSetDevice(job.dev));
   if (job.dev < 0 || job.dev >= 64) return fail(DECAES_EUNSUPPORTED, "device index %d out of range", job.dev);
@@ -1117,24 +1167,19 @@ static int run_slab(SlabJob &job, const double *image, int64_t Nvox, const decae
   Plan plan;
   int rc = make_plan(opts, part, job.dev, &plan);
   if (rc) return rc;
-  cudaStream_t st;
-  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  // one allocation for the slab: image + every requested output, all with stride nv
-  struct Field {
-    double *const *host;
-    int64_t mult;
-    size_t off;
-  };
   double *hostp[16] = {out->gdn, out->ggm, out->gva, out->fnr, out->snr, out->alpha, out->dist, out->resnorm,
                        out->decaycurve, out->mu, out->chi2factor, out->decaybasis, out->sfr, out->sgm, out->mfr, out->mgm};
   int64_t mult[16] = {1, 1, 1, 1, 1, 1, nT2, 1, nTE, 1, 1, (int64_t)nTE * nT2, 1, 1, 1, 1};
   if (!std::isnan(opts->SetFlipAngle)) hostp[11] = nullptr;  // shared basis is not a per-voxel output (:581-587)
   if (!part) hostp[12] = hostp[13] = hostp[14] = hostp[15] = nullptr;
+  // one allocation for the slab: image + every requested output (+ the Float32 copy of the image), all with stride nv
   size_t total = (size_t)nv * nTE, off[16];
   for (int f = 0; f < 16; f++) {
     off[f] = total;
     if (hostp[f]) total += (size_t)nv * mult[f];
   }
+  const size_t off_f32 = total;
+  if (img_f32) total += ((size_t)nv * nTE + 1) / 2;
   // The slab buffer is cached per device (grow-only, like the other workspaces): cudaMalloc + cudaFree of the 5.5 GB
   // of a full cfg3 volume cost more than the exposed copies.  decaes_release() or DECAES_SLAB_CACHE=0 give it back.
   static const bool cache_slab = !(getenv("DECAES_SLAB_CACHE") && atoi(getenv("DECAES_SLAB_CACHE")) == 0);
@@ -1150,57 +1195,180 @@ static int run_slab(SlabJob &job, const double *image, int64_t Nvox, const decae
   decaes_t2map_out dout;
   double **dptr = (double **)&dout;
   for (int f = 0; f < 16; f++) dptr[f] = hostp[f] ? dbuf + off[f] : nullptr;
-  // The slab is processed as up to DECAES_MAX_CHUNKS sub-slabs: all host-to-device copies are queued up front on
-  // a copy stream, the kernels run back to back on the compute stream as their inputs land, and every sub-slab's
-  // results go back while the next one computes.  Exposed transfer time = first copy in + last copy out.
-  int nchunks = (int)std::min<int64_t>(4, std::max<int64_t>(1, nv / 65536));
+  float *dimg32 = img_f32 ? (float *)(dbuf + off_f32) : nullptr;
+  const size_t elem = img_f32 ? sizeof(float) : sizeof(double);
+  const char *image = (const char *)image_any;
+
+  // pageable caller buffers -> pinned staging ring (DECAES_STAGING=0/1 overrides the detection)
+  bool staged = !host_ptr_is_pinned(image_any);
+  for (int f = 0; f < 16 && !staged; f++)
+    if (hostp[f] && !host_ptr_is_pinned(hostp[f])) staged = true;
+  if (const char *e = getenv("DECAES_STAGING")) staged = atoi(e) != 0;
+  job.st.pinned_staging = staged;
+
+  // Sub-slabs.  Exposed transfer time = first chunk in + last chunk out, so in staged mode (where the host packs and
+  // unpacks every byte) the first and the last chunk are made small.
+  int nchunks = (int)std::min<int64_t>(staged ? 8 : 4, std::max<int64_t>(1, nv / 65536));
   if (const char *e = getenv("DECAES_CHUNKS")) nchunks = std::max(1, std::min(DECAES_MAX_CHUNKS, atoi(e)));
   nchunks = (int)std::min<int64_t>(nchunks, nv);
-  cudaStream_t sc;
-  CUDA_TRY(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+  int64_t cb[DECAES_MAX_CHUNKS + 1];
+  {
+    double wsum = 0, acc = 0, wt[DECAES_MAX_CHUNKS];
+    for (int c = 0; c < nchunks; c++) wt[c] = (staged && nchunks >= 4 && (c == 0 || c + 1 == nchunks)) ? 0.25 : 1.0, wsum += wt[c];
+    cb[0] = 0;
+    for (int c = 0; c < nchunks; c++) acc += wt[c], cb[c + 1] = ((int64_t)((double)nv * acc / wsum) / DECAES_GROUP) * DECAES_GROUP;
+    cb[nchunks] = nv;
+    for (int c = 0; c < nchunks; c++) cb[c + 1] = std::max(cb[c + 1], cb[c]);
+  }
+  int64_t wmax = 0;
+  for (int c = 0; c < nchunks; c++) wmax = std::max(wmax, cb[c + 1] - cb[c]);
+
+  DeviceWs &dws = g_ws[job.dev];
+  if (staged) {
+    size_t slot = (size_t)32 << 20;
+    if (const char *e = getenv("DECAES_STAGE_MB")) slot = (size_t)std::max(1, atoi(e)) << 20;
+    slot = std::max(slot, (size_t)wmax * sizeof(double));
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    if ((rc = ring_ensure(dws, slot))) return rc;
+  }
+  cudaStream_t st, sc, sd;
+  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));  // kernels
+  CUDA_TRY(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));  // host -> device
+  CUDA_TRY(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));  // device -> host
   cudaEvent_t e0, e1, e2, e3, evin[DECAES_MAX_CHUNKS], evdone[DECAES_MAX_CHUNKS];
   cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventCreate(&e2), cudaEventCreate(&e3);
   for (int c = 0; c < nchunks; c++)
     cudaEventCreateWithFlags(&evin[c], cudaEventDisableTiming), cudaEventCreateWithFlags(&evdone[c], cudaEventDisableTiming);
-  auto bound = [&](int c) { return ((nv * c / nchunks) / DECAES_GROUP) * DECAES_GROUP; };
+
+  // ---- staging ring bookkeeping ----
+  struct Pending {
+    double *host;   // first destination row in the caller's array
+    int64_t w;      // doubles per row
+    int rows;
+    bool active;
+  } pend[DECAES_NSTAGE];
+  for (int s = 0; s < DECAES_NSTAGE; s++) pend[s].active = false;
+  int ring_next = 0;
+  auto acquire = [&]() -> int {  // next slot, free of device work and with its results handed to the caller
+    const int s = ring_next;
+    ring_next = (ring_next + 1) % DECAES_NSTAGE;
+    cudaEventSynchronize(dws.ring_ev[s]);
+    if (pend[s].active) {
+      const double *src = (const double *)dws.ring[s];
+      for (int r = 0; r < pend[s].rows; r++) memcpy(pend[s].host + (size_t)r * Nvox, src + (size_t)r * pend[s].w, (size_t)pend[s].w * sizeof(double));
+      pend[s].active = false;
+    }
+    return s;
+  };
+  auto t_host0 = std::chrono::steady_clock::now();
+  double staged_h2d_first_ms = 0, staged_d2h_last_ms = 0;
+
   CUDA_TRY(cudaEventRecord(e0, sc));
   for (int c = 0; c < nchunks; c++) {
-    const int64_t a = bound(c), b = (c + 1 == nchunks) ? nv : bound(c + 1);
-    CUDA_TRY(cudaMemcpy2DAsync(dbuf + a, nv * sizeof(double), image + job.v0 + a, Nvox * sizeof(double), (b - a) * sizeof(double),
-                               nTE, cudaMemcpyHostToDevice, sc));
-    if (opts->alpha_provided)
-      CUDA_TRY(cudaMemcpyAsync(dout.alpha + a, out->alpha + job.v0 + a, (b - a) * sizeof(double), cudaMemcpyHostToDevice, sc));
+    const int64_t a = cb[c], b = cb[c + 1], w = b - a;
+    if (w > 0) {
+      char *ddst = img_f32 ? (char *)(dimg32 + a) : (char *)(dbuf + a);
+      if (!staged) {
+        CUDA_TRY(cudaMemcpy2DAsync(ddst, nv * elem, image + (size_t)(job.v0 + a) * elem, Nvox * elem, w * elem, nTE,
+                                   cudaMemcpyHostToDevice, sc));
+        if (opts->alpha_provided)
+          CUDA_TRY(cudaMemcpyAsync(dout.alpha + a, out->alpha + job.v0 + a, w * sizeof(double), cudaMemcpyHostToDevice, sc));
+      } else {
+        const int rows_per_slot = (int)std::max<size_t>(1, dws.ring_cap / ((size_t)w * elem));
+        for (int r0 = 0; r0 < nTE; r0 += rows_per_slot) {
+          const int nr = std::min(rows_per_slot, nTE - r0);
+          const int sidx = acquire();
+          char *slotp = (char *)dws.ring[sidx];
+          for (int r = 0; r < nr; r++)
+            memcpy(slotp + (size_t)r * w * elem, image + ((size_t)(r0 + r) * Nvox + job.v0 + a) * elem, (size_t)w * elem);
+          CUDA_TRY(cudaMemcpy2DAsync(ddst + (size_t)r0 * nv * elem, nv * elem, slotp, w * elem, w * elem, nr, cudaMemcpyHostToDevice, sc));
+          CUDA_TRY(cudaEventRecord(dws.ring_ev[sidx], sc));
+        }
+        if (opts->alpha_provided) {
+          const int sidx = acquire();
+          memcpy(dws.ring[sidx], out->alpha + job.v0 + a, (size_t)w * sizeof(double));
+          CUDA_TRY(cudaMemcpyAsync(dout.alpha + a, dws.ring[sidx], w * sizeof(double), cudaMemcpyHostToDevice, sc));
+          CUDA_TRY(cudaEventRecord(dws.ring_ev[sidx], sc));
+        }
+      }
+    }
     CUDA_TRY(cudaEventRecord(evin[c], sc));
-    if (c == 0) CUDA_TRY(cudaEventRecord(e1, sc));
-  }
-  for (int c = 0; c < nchunks; c++) {
-    const int64_t a = bound(c), b = (c + 1 == nchunks) ? nv : bound(c + 1);
+    if (c == 0) {
+      CUDA_TRY(cudaEventRecord(e1, sc));
+      staged_h2d_first_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+    }
+    // the kernel of this chunk is enqueued as soon as its input is on its way
     decaes_t2map_out dc = dout;
     double **dcp = (double **)&dc;
     for (int f = 0; f < 16; f++)
       if (dcp[f]) dcp[f] += a;
     CUDA_TRY(cudaStreamWaitEvent(st, evin[c], 0));
-    rc = launch_pipeline(plan, job.dev, dbuf + a, b - a, nv, &dc, st, c);
-    if (rc) return rc;
+    if (w > 0) {
+      if (img_f32) {
+        f32_to_f64_kernel<<<(unsigned)((w + 255) / 256), 256, 0, st>>>(dimg32 + a, dbuf + a, w, nv, nTE);
+        CUDA_TRY(cudaGetLastError());
+        job.st.kernel_launches += 1;
+      }
+      rc = launch_pipeline(plan, job.dev, dbuf + a, w, nv, &dc, st, c);
+      if (rc) return rc;
+    }
     CUDA_TRY(cudaEventRecord(evdone[c], st));
-    CUDA_TRY(cudaStreamWaitEvent(sc, evdone[c], 0));
-    if (c + 1 == nchunks) CUDA_TRY(cudaEventRecord(e2, sc));
-    for (int f = 0; f < 16; f++)
-      if (hostp[f])
-        CUDA_TRY(cudaMemcpy2DAsync(hostp[f] + job.v0 + a, Nvox * sizeof(double), dptr[f] + a, nv * sizeof(double),
-                                   (b - a) * sizeof(double), mult[f], cudaMemcpyDeviceToHost, sc));
+    if (!staged) {
+      CUDA_TRY(cudaStreamWaitEvent(sd, evdone[c], 0));
+      if (c + 1 == nchunks) CUDA_TRY(cudaEventRecord(e2, sd));
+      for (int f = 0; f < 16; f++)
+        if (hostp[f] && w > 0)
+          CUDA_TRY(cudaMemcpy2DAsync(hostp[f] + job.v0 + a, Nvox * sizeof(double), dptr[f] + a, nv * sizeof(double),
+                                     w * sizeof(double), mult[f], cudaMemcpyDeviceToHost, sd));
+    }
   }
-  CUDA_TRY(cudaEventRecord(e3, sc));
+  if (staged) {
+    // results: chunk by chunk as the kernels finish, device -> slot -> caller's arrays, DECAES_NSTAGE - 1 slots in flight
+    for (int c = 0; c < nchunks; c++) {
+      const int64_t a = cb[c], b = cb[c + 1], w = b - a;
+      CUDA_TRY(cudaStreamWaitEvent(sd, evdone[c], 0));
+      auto t_last0 = std::chrono::steady_clock::now();
+      if (c + 1 == nchunks) {
+        CUDA_TRY(cudaEventRecord(e2, sd));
+        cudaEventSynchronize(evdone[c]);
+        t_last0 = std::chrono::steady_clock::now();
+      }
+      if (w > 0) {
+        const int rows_per_slot = (int)std::max<size_t>(1, dws.ring_cap / ((size_t)w * sizeof(double)));
+        for (int f = 0; f < 16; f++) {
+          if (!hostp[f]) continue;
+          for (int64_t r0 = 0; r0 < mult[f]; r0 += rows_per_slot) {
+            const int nr = (int)std::min<int64_t>(rows_per_slot, mult[f] - r0);
+            const int sidx = acquire();
+            CUDA_TRY(cudaMemcpy2DAsync(dws.ring[sidx], w * sizeof(double), dptr[f] + a + (size_t)r0 * nv, nv * sizeof(double),
+                                       w * sizeof(double), nr, cudaMemcpyDeviceToHost, sd));
+            CUDA_TRY(cudaEventRecord(dws.ring_ev[sidx], sd));
+            pend[sidx].host = hostp[f] + job.v0 + a + (size_t)r0 * Nvox, pend[sidx].w = w, pend[sidx].rows = nr, pend[sidx].active = true;
+          }
+        }
+      }
+      if (c + 1 == nchunks) {
+        for (int s = 0; s < DECAES_NSTAGE; s++) acquire();  // drain what is still in flight
+        staged_d2h_last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_last0).count();
+      }
+    }
+  }
+  CUDA_TRY(cudaEventRecord(e3, sd));
   CUDA_TRY(cudaStreamSynchronize(sc));
+  CUDA_TRY(cudaStreamSynchronize(sd));
   CUDA_TRY(cudaStreamSynchronize(st));
   float h2d = 0, d2h = 0;
   cudaEventElapsedTime(&h2d, e0, e1), cudaEventElapsedTime(&d2h, e2, e3);
-  job.st.h2d_ms = h2d, job.st.d2h_ms = d2h;  // exposed parts: first sub-slab in, last sub-slab out
+  // exposed parts: first sub-slab in, last sub-slab out (staged mode: host wall time of the same two steps)
+  job.st.h2d_ms = staged ? staged_h2d_first_ms : h2d, job.st.d2h_ms = staged ? staged_d2h_last_ms : d2h;
+  const int extra_launches = job.st.kernel_launches;
   rc = collect_device_stats(job.dev, &job.st);
+  (void)extra_launches;
   cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2), cudaEventDestroy(e3);
   for (int c = 0; c < nchunks; c++) cudaEventDestroy(evin[c]), cudaEventDestroy(evdone[c]);
   if (!cache_slab) cudaFree(dbuf);
   cudaStreamDestroy(sc);
+  cudaStreamDestroy(sd);
   cudaStreamDestroy(st);
   return rc;
 }
@@ -1216,19 +1384,67 @@ void decaes_release(void) {
   cudaGetDevice(&cur);
   for (int d = 0; d < ndev && d < 64; d++) {
     DeviceWs &ws = g_ws[d];
-    if (!(ws.slab || ws.scratch || ws.basis_rm || ws.basis_cm || ws.gram_set)) continue;
+    if (!(ws.slab || ws.scratch || ws.basis_rm || ws.basis_cm || ws.gram_set || ws.ring[0])) continue;
     cudaSetDevice(d);
     cudaDeviceSynchronize();
     cudaFree(ws.slab), cudaFree(ws.scratch), cudaFree(ws.basis_rm), cudaFree(ws.basis_cm), cudaFree(ws.dbasis_cm), cudaFree(ws.gram_set);
     ws.slab = ws.scratch = ws.basis_rm = ws.basis_cm = ws.dbasis_cm = ws.gram_set = nullptr;
+    for (int r = 0; r < DECAES_NSTAGE; r++) {
+      if (ws.ring[r]) cudaFreeHost(ws.ring[r]);
+      ws.ring[r] = nullptr;
+    }
+    ws.ring_cap = 0;
     ws.slab_cap = ws.scratch_cap = ws.basis_rm_cap = ws.basis_cm_cap = ws.gram_cap = 0;
   }
   cudaSetDevice(cur);
 }
 
 
-int decaes_t2map(const double *image, const decaes_t2map_opts *opts, const decaes_t2part_opts *part,
-                 const decaes_t2map_out *out) {
+// Slab boundaries for `ng` devices.  Work is proportional to the number of voxels above Threshold
+// (src/T2mapSEcorr.jl:177), not to the number of voxels: a brain-masked volume is 60-70 % background and the
+// background is not spread evenly over the slowest dimension, so equal-length slabs would leave the devices that own
+// the top and bottom slices idle.  One pass over the first echo counts foreground voxels per block of 1024 and the
+// cuts are placed on the block boundaries that split the COUNT evenly (an unmasked volume gives equal lengths).
+extern "C++" {
+template <typename T>
+static void balanced_bounds(const T *first_echo, int64_t Nvox, double threshold, int ng, std::vector<int64_t> &cut) {
+  const int64_t B = 1024, nb = (Nvox + B - 1) / B;
+  std::vector<int64_t> cnt((size_t)nb + 1, 0);
+  const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(8, nb / 256));
+  auto work = [&](int t) {
+    for (int64_t k = nb * t / nthreads; k < nb * (t + 1) / nthreads; k++) {
+      int64_t c = 0;
+      const int64_t e = std::min(Nvox, (k + 1) * B);
+      for (int64_t v = k * B; v < e; v++) c += ((double)first_echo[v] > threshold);
+      cnt[(size_t)k + 1] = c;
+    }
+  };
+  if (nthreads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+  }
+  for (int64_t k = 0; k < nb; k++) cnt[(size_t)k + 1] += cnt[(size_t)k];
+  const int64_t totalfg = cnt[(size_t)nb];
+  cut.assign((size_t)ng + 1, 0);
+  cut[(size_t)ng] = Nvox;
+  for (int d = 1; d < ng; d++) {
+    if (totalfg == 0) {
+      cut[(size_t)d] = ((Nvox * d / ng) / DECAES_GROUP) * DECAES_GROUP;
+      continue;
+    }
+    const int64_t want = totalfg * d / ng;
+    const int64_t k = std::lower_bound(cnt.begin(), cnt.end(), want) - cnt.begin();
+    cut[(size_t)d] = std::min(Nvox, k * B);  // B is a multiple of the 4-voxel work group
+  }
+  for (int d = 1; d <= ng; d++) cut[(size_t)d] = std::max(cut[(size_t)d], cut[(size_t)d - 1]);
+}
+}  // extern "C++"
+
+static int t2map_host(const void *image, bool img_f32, const decaes_t2map_opts *opts, const decaes_t2part_opts *part,
+                      const decaes_t2map_out *out) {
   std::lock_guard<std::mutex> lk(g_call_mutex);
   auto t0 = std::chrono::steady_clock::now();
   int rc = validate_map(opts);
@@ -1243,14 +1459,22 @@ int decaes_t2map(const double *image, const decaes_t2map_opts *opts, const decae
   int cur = 0;
   cudaGetDevice(&cur);
   std::vector<SlabJob> jobs(ng);
-  // contiguous voxel slabs, boundaries aligned to the 4-voxel work group
+  // contiguous voxel slabs, boundaries aligned to the 4-voxel work group; equal foreground counts when a
+  // threshold is in force and more than one device takes part
+  std::vector<int64_t> cut;
+  const bool balance = ng > 1 && opts->Threshold > -INFINITY && !(getenv("DECAES_BALANCE") && atoi(getenv("DECAES_BALANCE")) == 0);
+  if (balance) {
+    if (img_f32) balanced_bounds((const float *)image, Nvox, opts->Threshold, ng, cut);
+    else balanced_bounds((const double *)image, Nvox, opts->Threshold, ng, cut);
+  }
   for (int d = 0; d < ng; d++) {
     int64_t a = 0, b = 0;
-    decaes_slab_bounds(Nvox, ng, d, &a, &b);
+    if (balance) a = cut[(size_t)d], b = cut[(size_t)d + 1];
+    else decaes_slab_bounds(Nvox, ng, d, &a, &b);
     jobs[d].dev = (ng == 1) ? cur : d, jobs[d].v0 = a, jobs[d].v1 = b, jobs[d].rc = 0, jobs[d].err[0] = 0;
   }
   auto worker = [&](SlabJob &j) {
-    j.rc = run_slab(j, image, Nvox, opts, part, out);
+    j.rc = run_slab(j, image, img_f32, Nvox, opts, part, out);
     if (j.rc) snprintf(j.err, sizeof j.err, "%s", g_err);
   };
   if (ng == 1) {
@@ -1276,6 +1500,37 @@ int decaes_t2map(const double *image, const decaes_t2map_opts *opts, const decae
   }
   g_stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return DECAES_OK;
+}
+
+int decaes_slab_bounds_masked(const double *first_echo, int64_t nvox, double threshold, int32_t nshards, int64_t *cuts) {
+  if (!first_echo || !cuts || nvox < 0 || nshards < 1) return fail(DECAES_EINVAL, "bad slab arguments");
+  std::vector<int64_t> cut;
+  balanced_bounds(first_echo, nvox, threshold, nshards, cut);
+  for (int d = 0; d <= nshards; d++) cuts[d] = cut[(size_t)d];
+  return DECAES_OK;
+}
+
+int decaes_t2map(const double *image, const decaes_t2map_opts *opts, const decaes_t2part_opts *part,
+                 const decaes_t2map_out *out) {
+  return t2map_host(image, false, opts, part, out);
+}
+
+int decaes_t2map_f32(const float *image, const decaes_t2map_opts *opts, const decaes_t2part_opts *part,
+                     const decaes_t2map_out *out) {
+  return t2map_host(image, true, opts, part, out);
+}
+
+void *decaes_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    fail(DECAES_ENOMEM, "cudaHostAlloc of %zu bytes failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+void decaes_host_free(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 int decaes_t2part(const double *dist, const decaes_t2part_opts *part, double *sfr, double *sgm, double *mfr,

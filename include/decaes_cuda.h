@@ -38,6 +38,7 @@
 #ifndef DECAES_CUDA_H
 #define DECAES_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -136,8 +137,23 @@ int decaes_t2map(const double *image, const decaes_t2map_opts *opts,
                  const decaes_t2part_opts *part /* NULL = no fused T2part */,
                  const decaes_t2map_out *out);
 
+/* Same call for a Float32 volume: the image is converted to Float64 on the device (exact), everything downstream -
+ * arithmetic and outputs - is Float64.  It stands for load_image's copyto!(Array{Float64,4}(undef, sz), data)
+ * (src/main.jl:612-617) followed by T2mapSEcorr, with half the host-to-device traffic. */
+int decaes_t2map_f32(const float *image, const decaes_t2map_opts *opts,
+                     const decaes_t2part_opts *part, const decaes_t2map_out *out);
+
 int decaes_t2part(const double *dist, const decaes_t2part_opts *part,
                   double *sfr, double *sgm, double *mfr, double *mgm);
+
+/* Host buffers.  The host entry points accept ANY host memory.  Page-locked buffers (decaes_host_alloc,
+ * cudaHostAlloc, cudaHostRegister) are copied directly; pageable ones - ordinary Julia Arrays - are staged through a
+ * pinned ring the library owns (4 x 32 MB per device, DECAES_STAGE_MB), packed / unpacked by the calling host thread
+ * while the neighbouring sub-slab computes.  decaes_run_stats.pinned_staging tells which path ran.
+ * With more than one device and a finite Threshold the slabs are cut so that every device gets the same number of
+ * voxels above Threshold (one pass over the first echo), not the same number of voxels. */
+void *decaes_host_alloc(size_t bytes); /* page-locked, portable across devices; NULL on failure */
+void decaes_host_free(void *p);
 
 /* echotimes[nTE], t2times[nT2], refangleset[nRefAngles or 1],
  * decaybasisset[nTE*nT2*nRefAngles] (or nTE*nT2 with SetFlipAngle); any may be NULL. */
@@ -166,6 +182,11 @@ int decaes_mock_image_device(double *d_image, int64_t nvox, int64_t stride, int6
  * 4-voxel work group; the last shard takes the remainder).  Pure host arithmetic: this is the
  * whole multi-GPU "protocol" of the path — shards are independent and there is no collective. */
 int decaes_slab_bounds(int64_t nvox, int32_t nshards, int32_t index, int64_t *v0, int64_t *v1);
+
+/* The cuts decaes_t2map uses when ngpus > 1 and Threshold is finite: cuts[0..nshards], cuts[d] .. cuts[d+1] is shard
+ * d; every shard holds (to within one 1024-voxel block) the same number of voxels with first_echo[v] > threshold
+ * (src/T2mapSEcorr.jl:177 is the filter).  Pure host arithmetic. */
+int decaes_slab_bounds_masked(const double *first_echo, int64_t nvox, double threshold, int32_t nshards, int64_t *cuts);
 
 /* ---- misc ---- */
 const char *decaes_last_error(void);

@@ -14,14 +14,21 @@ pytestmark = pytest.mark.gpu
 
 # (name, nTE, TE, nT2, Reg, extra opts, part windows, nvox, max fraction out of tolerance)
 CONFIGS = [
-    ("cfg1_none", 32, 10e-3, 40, "none", {}, {}, 4096, 0.01),
-    ("cfg2_lcurve48", 48, 8e-3, 40, "lcurve", {}, {}, 1024, 0.02),
-    ("cfg3_lcurve56", 56, 7e-3, 40, "lcurve", {}, {}, 1024, 0.02),
-    ("cfg4_chi2", 48, 8e-3, 60, "chi2", {"Chi2Factor": 1.02}, {}, 1024, 0.02),
-    ("cfg4_gcv", 48, 8e-3, 60, "gcv", {}, {}, 256, 0.03),
-    ("cfg5_mdp", 32, 10e-3, 60, "mdp", {"NoiseLevel": 1e-3}, {"SPWin": (10e-3, 200e-3), "MPWin": (200e-3, 2.0)}, 1024,
-     0.02),
+    ("cfg1_none", 32, 10e-3, 40, "none", {}, {}, 4096, 0.0),
+    ("cfg2_lcurve48", 48, 8e-3, 40, "lcurve", {}, {}, 16384, 0.0),
+    ("cfg3_lcurve56", 56, 7e-3, 40, "lcurve", {}, {}, 16384, 0.0),
+    ("cfg4_chi2", 48, 8e-3, 60, "chi2", {"Chi2Factor": 1.02}, {}, 4096, 0.0),
+    ("cfg4_gcv", 48, 8e-3, 60, "gcv", {}, {}, 2048, 0.0),
+    ("cfg5_mdp", 32, 10e-3, 60, "mdp", {"NoiseLevel": 1e-3}, {"SPWin": (10e-3, 200e-3), "MPWin": (200e-3, 2.0)}, 4096,
+     0.0),
 ]
+
+
+def flip_bound(own, n):
+    """mu-search flips allowed for the GPU: the rate at which two CPU builds of the oracle (sequential vs vectorised
+    @simd reductions, oracle/Makefile) disagree on the SAME voxels, + 15 % + three sigmas of sampling noise."""
+    import math
+    return 1.15 * own + 3.0 * math.sqrt(max(own, 1.0 / n) * (1 - own) / n)
 
 
 def gpu_t2map(pkg, orc, img, o, p, **alloc_kw):
@@ -45,17 +52,21 @@ def test_gpu_matches_oracle(pkg, orc, name, nTE, TE, nT2, Reg, extra, part_kw, n
     ref, st = orc.t2map(img, o, p)
     got = gpu_t2map(pkg, orc, img, o, p)
     rep = parity.compare(ref, got)
-    print(name, rep, "oracle early returns:", st.early_returns)
+    own = 0.0
+    if Reg != "none":
+        alt, _ = orc.t2map(img, o, p, L=orc.lib_variant("simd"))
+        own = parity.compare(ref, alt)["mu_flip_frac"]
+    print(name, rep, "oracle early returns:", st.early_returns, "two-CPU-builds flip rate:", own)
     assert rep["nan_mismatch"] == 0
-    # voxels that selected the same regularisation parameter must meet the north_star tolerances
-    # (a handful of active-set flips allowed and counted) ...
-    assert rep["frac_out_of_tolerance_same_mu"] <= maxfrac, rep
-    # ... and the rate of search-path flips must not exceed the oracle's own sensitivity to a 1-ulp
-    # input perturbation (tests/test_oracle_sensitivity.py: 3-4 % for lcurve)
-    assert rep["mu_flip_frac"] <= (0.0 if Reg == "none" else 0.08), rep
+    # every voxel that selected the same regularisation parameter meets the north_star tolerances ...
+    assert rep["frac_out_of_tolerance_same_mu"] <= maxfrac and rep["support_diff"] == 0, rep
+    # ... and the mu searches (chaotic at their 1e-4 termination width, tests/test_oracle_sensitivity.py) do not flip
+    # more often than two CPU builds of the same algorithm do on these very voxels
+    assert rep["mu_flip_frac"] <= flip_bound(own, nvox), (own, rep)
     assert rep.get("mu_flip_median_dlog", 0.0) < 5e-3, rep
     stats = pkg.last_stats()
     assert stats["voxels_processed"] == nvox and stats["kernel_launches"] >= 2
+    assert stats["lcurve_overflow"] == 0 and stats["nnls_itercap"] == 0 and stats["early_returns"] == st.early_returns, stats
 
 
 # legacy = true (src/types.jl:20-21, 59-63): every angle of an 8-point grid is probed, the flip angle is the sampled
@@ -177,15 +188,21 @@ def test_refcon_angle(pkg, orc, beta, Reg):
 
 @pytest.mark.parametrize("nTE,nT2", [(4, 2), (5, 3), (8, 8), (47, 47), (64, 60)])
 def test_odd_sizes(pkg, orc, nTE, nT2):
-    nvox = 64
+    nvox = 256
     img = orc.mock_image(nvox, nTE, 10e-3, seed=nTE)
     for Reg, extra in [("none", {}), ("lcurve", {}), ("chi2", {"Chi2Factor": 1.05}), ("mdp", {"NoiseLevel": 1e-2})]:
         o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, 10e-3, Reg=Reg, ngpus=1, **extra)
         ref, _ = orc.t2map(img, o)
         got = gpu_t2map(pkg, orc, img, o, None)
         rep = parity.compare(ref, got)
+        own = 0.0
+        if Reg != "none":
+            alt, _ = orc.t2map(img, o, L=orc.lib_variant("simd"))
+            own = parity.compare(ref, alt)["mu_flip_frac"]
         assert rep["nan_mismatch"] == 0
-        assert rep["frac_out_of_tolerance_same_mu"] <= 0.1 and rep["mu_flip_frac"] <= 0.2, (Reg, rep)
+        # north_star bounds: same mu => within tolerance; flips no more frequent than between two CPU builds (64 voxels:
+        # one extra voxel of slack)
+        assert rep["out_of_tolerance_same_mu"] <= 1 and rep["mu_flip_frac"] <= own + 2.0 / nvox, (Reg, own, rep)
 
 
 def test_t2part_standalone_bit_exact_structure(pkg, orc):
@@ -319,3 +336,30 @@ def test_pathological_voxels_terminate_and_stay_local(pkg, orc, Reg, extra):
         assert np.isnan(got["gdn"][4]) == np.isnan(ref["gdn"][4])
         for v in (6, 7):  # power-of-ten scalings: scale-free maps equal those of the unscaled voxel
             assert abs(got["ggm"][v] - base["ggm"][v]) <= 1e-6 * max(1.0, abs(base["ggm"][v])) or Reg == "lcurve"
+
+
+def test_fused_sigmoid_epilogue(pkg, orc):
+    """Sigmoid-weighted small-pool fraction (src/T2partSEcorr.jl:155-164) in the FUSED T2part epilogue of the pipeline
+    kernel: equal to the oracle and to the standalone T2partSEcorr kernel applied to the stored distributions."""
+    nvox, nTE, nT2, TE = 2048, 48, 40, 8e-3
+    img = orc.mock_image(nvox, nTE, TE, seed=41)
+    o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, TE, Reg="chi2", Chi2Factor=1.02, ngpus=1)
+    for Sigmoid in (5e-3, 20e-3):
+        p = orc.make_t2part_opts((nvox, 1, 1), nT2, SPWin=(10e-3, 40e-3), MPWin=(40e-3, 200e-3), Sigmoid=Sigmoid)
+        ref, _ = orc.t2map(img, o, p)
+        got = gpu_t2map(pkg, orc, img, o, p)
+        rep = parity.compare(ref, got)
+        assert rep["out_of_tolerance_same_mu"] == 0 and rep["sfr_fail"] <= rep["mu_flips"], rep
+        hard = orc.make_t2part_opts((nvox, 1, 1), nT2, SPWin=(10e-3, 40e-3), MPWin=(40e-3, 200e-3))
+        assert np.abs(got["sfr"] - gpu_t2map(pkg, orc, img, o, hard)["sfr"]).max() > 1e-4  # the weights do something
+        outs = {k: np.full(nvox, np.nan) for k in orc.PART_NAMES}
+        d = np.asfortranarray(got["dist"])
+        rc = pkg.lib().decaes_t2part(d.ctypes.data, C.byref(p), *[outs[k].ctypes.data for k in orc.PART_NAMES])
+        assert rc == 0
+        for k in orc.PART_NAMES:
+            np.testing.assert_allclose(outs[k], got[k], rtol=1e-12, equal_nan=True, err_msg=k)
+    # a fused T2part with another T2Range than the map's is refused (it would silently use the map's grid)
+    bad = orc.make_t2part_opts((nvox, 1, 1), nT2, T2Range=(8e-3, 2.0))
+    arrs, out = orc.alloc_outputs(nvox, nTE, nT2, part=True)
+    assert pkg.lib().decaes_t2map(img.ctypes.data, C.byref(o), C.byref(bad), C.byref(out)) == -1
+    assert b"T2Range" in pkg.lib().decaes_last_error()
