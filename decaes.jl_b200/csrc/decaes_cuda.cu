@@ -314,6 +314,7 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
     if (W.n_early) atomicAdd(&P.counters[2], W.n_early);
     if (W.n_overflow) atomicAdd(&P.counters[3], W.n_overflow);
     if (W.n_itercap) atomicAdd(&P.counters[26], W.n_itercap);
+    if (W.n_polish) atomicAdd(&P.counters[27], W.n_polish);
   }
 }
 
@@ -908,6 +909,8 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
   st->pipeline_ms = std::max(st->pipeline_ms, (double)b);
   st->voxels_processed += (int64_t)c[1];
   st->early_returns += (int64_t)c[2], st->lcurve_overflow += (int64_t)c[3], st->nnls_itercap += (int64_t)c[26];
+  if (getenv("DECAES_PHASE_CYCLES"))
+    fprintf(stderr, "[decaes] KKT-polish resumptions per voxel: %.4f\n", (double)c[27] / std::max<double>(1.0, (double)c[1]));
   if (getenv("DECAES_PHASE_CYCLES"))
     fprintf(stderr, "[decaes] warp-cycles per voxel: barrier %.0f  flip-angle %.0f  basis %.0f  solve+save %.0f  total %.0f\n",
             (double)c[4] / std::max<double>(1.0, (double)c[1]), (double)c[5] / std::max<double>(1.0, (double)c[1]),

@@ -181,7 +181,7 @@ struct Warp {
   int dirty_rows;   // lambda rows of the working matrix that may be non-zero
   int cur_slot;     // 0-based current cache slot (persists across voxels like work.idx[])
   int lane;
-  unsigned long long n_early, n_overflow, n_itercap;
+  unsigned long long n_early, n_overflow, n_itercap, n_polish;
   int nsolve_voxel = 0, nunreg_voxel = 0;  // Tikhonov / unregularised solves of the current voxel (DECAES_PROFILE)
 
   __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
@@ -211,7 +211,7 @@ struct Warp {
     dirty_rows = p.rows_alloc - p.nTE;
     cur_slot = 0;
     lane = lane_id();
-    n_early = n_overflow = n_itercap = 0;
+    n_early = n_overflow = n_itercap = n_polish = 0;
   }
 
   // ---- TMA: stage one nTE x nT2 matrix (row-major, ld) from global into the working matrix ----
@@ -1121,12 +1121,15 @@ struct Warp {
   // memory; A itself stays in the warp's global scratch (L2) in both layouts and is only read for
   // explicit residuals (||Ax - b||^2, iterative refinement, fitted curve).
   // =====================================================================================
-  // c = A' bd  (lane <-> column, coalesced rows of the row-major matrix)
-  __device__ __noinline__ void gram_rhs(const double *Arm) {
+  // out = A' vec  (lane <-> column, coalesced rows of the row-major matrix); gram_rhs: c = A' bd
+  __device__ __forceinline__ void gram_rhs(const double *Arm) { gram_atv(Arm, this->bd, this->cvec); }
+  __device__ __noinline__ void gram_atv(const double *Arm, const double *vec, double *outv) {
     GL(Arm);
     const int lane = this->lane;
-    VIEW(double, bd);
-    VIEW(double, cvec);
+    const double *const bd = vec;
+    double *const cvec = outv;
+    SH(bd);
+    SH(cvec);
     const int nTE = cP.nTE, ld = cP.ld, n = cP.nT2;
     // lane <-> columns lane and lane + 32: both advance together, 16 loads in flight (the matrix lives in L2)
     const double *c0 = Arm + (lane < n ? lane : 0), *c1 = Arm + (lane + 32 < n ? lane + 32 : 0);
@@ -1249,6 +1252,52 @@ struct Warp {
       PROF_BEGIN(2);
       r2 = gram_residual(src.Acm, o.k);
       PROF_END(2);
+    }
+    // KKT polish.  The active-set decisions above were taken on normal-equation quantities: the dual w = c - G_P s
+    // carries ~cond(A_P)^2 eps of noise (1e-10 on long-T2 pools), so a column whose true dual is a small positive
+    // number can be left out (or a coefficient that should be clamped kept in) - a slightly worse stationary point
+    // where the reference's QR iteration, whose duals are good to ~1e-15, goes on.  With the refined solution and
+    // its explicit residual in hand, the dual is recomputed EXPLICITLY (w = A'r, one pass over the basis) and the
+    // iteration resumes from here until the reference's own termination test - no positive dual, all coefficients
+    // positive - holds at that accuracy.  Almost every solve passes at once.
+    unsigned long long tried = 0ull;
+    _Pragma("unroll 1") for (int round = 0; round < 6; round++) {
+      PROF_BEGIN(0);
+      gram_atv(src.Arm, fit, gws.w);
+      unsigned long long key = 0ull, best;
+      int bj = 0x7fffffff;
+      _Pragma("unroll 1") for (int j = lane; j < cP.nT2; j += 32) {
+        const double wj = gws.w[j];
+        const unsigned long long kb = (unsigned long long)__double_as_longlong(wj);
+        if (!(((o.mask | tried) >> j) & 1ull) && wj > 0.0 && kb > key) key = kb, bj = j;
+      }
+      bj = warp_argmax_bits(key, bj, best);
+      unsigned long long neg = 0ull;
+      _Pragma("unroll 1") for (int t = lane; t < o.k; t += 32)
+        if (!(gws.s[t] > 0.0)) neg |= 1ull << gws.P[t];
+      neg = warp_or64(neg);
+      PROF_END(0);
+      if (best == 0ull && neg == 0ull) break;
+      if (o.k >= max_set && neg == 0ull) break;
+      unsigned long long m2 = o.mask & ~neg;
+      if (best != 0ull && __popcll(m2) < max_set) m2 |= 1ull << bj, tried |= 1ull << bj;
+      _Pragma("unroll 1") for (int j = lane; j < cP.nT2; j += 32) {
+        const double xj = gws.x[j];
+        gws.x[j] = (((m2 >> j) & 1ull) && xj > 0.0) ? xj : 0.0;
+      }
+      __syncwarp();
+      if (m2 == 0ull) {
+        o = gram_nnls<VS>(V, cP.nT2, cP.ldg, 0.0, max_set, false, 0ull);
+      } else {
+        o = gram_nnls<VS>(V, cP.nT2, cP.ldg, 0.0, max_set, true, m2);
+      }
+      n_itercap += o.capped;
+      r2 = gram_residual(src.Acm, o.k);
+      if (o.k > 0) {
+        gram_refine(src.Acm, o.k, 0.0);
+        r2 = gram_residual(src.Acm, o.k);
+      }
+      n_polish++;
     }
     return r2;
   }
