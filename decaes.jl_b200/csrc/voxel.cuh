@@ -1218,6 +1218,49 @@ struct Warp {
     __syncwarp();
   }
 
+  // Explicit duals of the columns whose normal-equation dual (left in gws.w by gram_nnls) is not clearly negative:
+  // w_j = A_j' r with r = b - A_P s in `fit`.  Returns the column with the largest positive explicit dual (first on
+  // ties, like largest_positive_dual, src/NNLS.jl:541-554) or -1.  "Clearly negative" = below -1e-6 max|c|: four orders
+  // of magnitude above the noise the normal-equation dual was seen to carry.  lane <-> echo, up to four columns per
+  // L2 round trip, butterfly sums interleaved for instruction-level parallelism.
+  __device__ __noinline__ int kkt_pick(const double *Acm, unsigned long long excl) {
+    GL(Acm);
+    const int lane = this->lane;
+    VIEW(double, fit);
+    VIEW(double, cvec);
+    VIEW_GWS();
+    const int nTE = cP.nTE, n = cP.nT2;
+    const int j0 = lane < n ? lane : 0, j1 = lane + 32 < n ? lane + 32 : 0;
+    const double tau = -1e-6 * warp_max(fmax(lane < n ? fabs(cvec[j0]) : 0.0, lane + 32 < n ? fabs(cvec[j1]) : 0.0));
+    const unsigned c0 = __ballot_sync(DECAES_FULL_MASK, lane < n && !((excl >> j0) & 1ull) && gws.w[j0] > tau);
+    const unsigned c1 = __ballot_sync(DECAES_FULL_MASK, lane + 32 < n && !((excl >> j1) & 1ull) && gws.w[j1] > tau);
+    unsigned long long cand = ((unsigned long long)c1 << 32) | c0;
+    const int i0 = lane < nTE ? lane : 0, i1 = lane + 32 < nTE ? lane + 32 : i0, i2 = lane + 64 < nTE ? lane + 64 : i0;
+    const double r0 = lane < nTE ? fit[i0] : 0.0, r1 = lane + 32 < nTE ? fit[i1] : 0.0, r2 = lane + 64 < nTE ? fit[i2] : 0.0;
+    double best = 0.0;
+    int bj = -1;
+    _Pragma("unroll 1") while (cand) {
+      int jc[4];
+      double a[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        jc[q] = cand ? __ffsll((long long)cand) - 1 : -1;
+        if (cand) cand &= cand - 1;
+        const double *col = Acm + (jc[q] >= 0 ? jc[q] : 0) * nTE;
+        a[q] = fma(col[i0], r0, fma(col[i1], r1, __dmul_rn(col[i2], r2)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) a[q] += __shfl_xor_sync(DECAES_FULL_MASK, a[q], o);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (jc[q] >= 0 && a[q] > best) best = a[q], bj = jc[q];
+    }
+    return bj;
+  }
+
   // unregularised NNLS following the reference's cold-start path, polished by one refinement step;
   // returns ||A x - b||^2 (explicit) and leaves r in `fit`, x in gws.x, the active set in gws.cP.
   // `warm_mask` != 0: start from that active set instead (flip-angle probes only: the loss and its
@@ -1257,40 +1300,27 @@ struct Warp {
     // carries ~cond(A_P)^2 eps of noise (1e-10 on long-T2 pools), so a column whose true dual is a small positive
     // number can be left out (or a coefficient that should be clamped kept in) - a slightly worse stationary point
     // where the reference's QR iteration, whose duals are good to ~1e-15, goes on.  With the refined solution and
-    // its explicit residual in hand, the dual is recomputed EXPLICITLY (w = A'r, one pass over the basis) and the
-    // iteration resumes from here until the reference's own termination test - no positive dual, all coefficients
-    // positive - holds at that accuracy.  Almost every solve passes at once.
+    // its explicit residual in hand, the duals that are not clearly negative are recomputed EXPLICITLY (w_j = A_j'r)
+    // and the iteration resumes from here until the reference's own termination test - no positive dual, all
+    // coefficients positive - holds at that accuracy.  Almost every solve passes at once (kkt_pick: one L2 round trip).
     unsigned long long tried = 0ull;
     _Pragma("unroll 1") for (int round = 0; round < 6; round++) {
       PROF_BEGIN(0);
-      gram_atv(src.Arm, fit, gws.w);
-      unsigned long long key = 0ull, best;
-      int bj = 0x7fffffff;
-      _Pragma("unroll 1") for (int j = lane; j < cP.nT2; j += 32) {
-        const double wj = gws.w[j];
-        const unsigned long long kb = (unsigned long long)__double_as_longlong(wj);
-        if (!(((o.mask | tried) >> j) & 1ull) && wj > 0.0 && kb > key) key = kb, bj = j;
-      }
-      bj = warp_argmax_bits(key, bj, best);
+      const int bj = (o.k < max_set) ? kkt_pick(src.Acm, o.mask | tried) : -1;
       unsigned long long neg = 0ull;
       _Pragma("unroll 1") for (int t = lane; t < o.k; t += 32)
         if (!(gws.s[t] > 0.0)) neg |= 1ull << gws.P[t];
       neg = warp_or64(neg);
       PROF_END(0);
-      if (best == 0ull && neg == 0ull) break;
-      if (o.k >= max_set && neg == 0ull) break;
+      if (bj < 0 && neg == 0ull) break;
       unsigned long long m2 = o.mask & ~neg;
-      if (best != 0ull && __popcll(m2) < max_set) m2 |= 1ull << bj, tried |= 1ull << bj;
+      if (bj >= 0) m2 |= 1ull << bj, tried |= 1ull << bj;
       _Pragma("unroll 1") for (int j = lane; j < cP.nT2; j += 32) {
         const double xj = gws.x[j];
         gws.x[j] = (((m2 >> j) & 1ull) && xj > 0.0) ? xj : 0.0;
       }
       __syncwarp();
-      if (m2 == 0ull) {
-        o = gram_nnls<VS>(V, cP.nT2, cP.ldg, 0.0, max_set, false, 0ull);
-      } else {
-        o = gram_nnls<VS>(V, cP.nT2, cP.ldg, 0.0, max_set, true, m2);
-      }
+      o = gram_nnls<VS>(V, cP.nT2, cP.ldg, 0.0, max_set, m2 != 0ull, m2);
       n_itercap += o.capped;
       r2 = gram_residual(src.Acm, o.k);
       if (o.k > 0) {
