@@ -75,11 +75,42 @@ function CT2partOpts(o::T2partOptions{Float64})
     return CT2partOpts(o.MatrixSize..., o.nT2, o.T2Range..., o.SPWin..., o.MPWin..., nan_if_nothing(o.Sigmoid))
 end
 
-function check_status(status::Cint)
-    status == 0 && return nothing
-    msg = unsafe_string(ccall((:decaes_last_error, libdecaes_cuda), Cstring, ()))
-    return error("libdecaes_cuda failed with status $status: $msg")
+# decaes_run_stats (ABI v2) — timings and the voxels the north star wants "counted and reported"
+struct CRunStats
+    voxels_total::Int64; voxels_processed::Int64
+    ngpus_used::Int32; kernel_launches::Int32
+    setup_ms::Float64; pipeline_ms::Float64; h2d_ms::Float64; d2h_ms::Float64; total_ms::Float64
+    early_returns::Int64      # chi2 / MDP early-return voxels (reference-undefined: src/lsqnonneg.jl:510-515, 708-718)
+    lcurve_overflow::Int64    # L-curve searches that outgrew the per-voxel caches (0 expected)
+    nnls_itercap::Int64       # NNLS solves stopped by the 3n iteration cap
+    pinned_staging::Int64     # 1: pageable arrays were staged through the library's pinned ring
 end
+
+"""
+    last_stats() -> CRunStats
+
+Statistics of the last library call made by this thread (`decaes_get_stats`).
+"""
+function last_stats()
+    st = Ref{CRunStats}()
+    ccall((:decaes_get_stats, libdecaes_cuda), Cvoid, (Ref{CRunStats},), st)
+    return st[]
+end
+
+const DECAES_ECUDA = Cint(-2)        # no usable device / CUDA error
+const DECAES_EUNSUPPORTED = Cint(-3) # outside the accelerated path: nT2 > 64, nRefAngles > 64, nTE > 72
+
+last_error() = unsafe_string(ccall((:decaes_last_error, libdecaes_cuda), Cstring, ()))
+
+# `true`: done on the GPU; `false`: the library declined (no device, unsupported size) and the caller should run
+# DECAES.jl's own CPU method; anything else is an error.
+function check_status(status::Cint)
+    status == 0 && return true
+    (status == DECAES_EUNSUPPORTED || status == DECAES_ECUDA) && return false
+    return error("libdecaes_cuda failed with status $status: $(last_error())")
+end
+
+gpu_available() = ccall((:decaes_device_count, libdecaes_cuda), Cint, ()) > 0
 
 """
     t2map_gpu!(maps, dist, image, opts; ngpus = 0)
@@ -101,10 +132,65 @@ function t2map_gpu!(maps::T2Maps{Float64}, dist::T2Distributions{Float64}, image
         status = ccall((:decaes_t2map, libdecaes_cuda), Cint,
             (Ptr{Float64}, Ref{CT2mapOpts}, Ptr{Cvoid}, Ref{CT2mapOut}),
             image, copts, C_NULL, out)
-        check_status(status)
+        if !check_status(status)
+            # not accelerated (e.g. nT2 = 120, a 96-echo train, no GPU in this machine): the reference's CPU worker loop
+            @warn "libdecaes_cuda declined ($(last_error())); running DECAES.jl's CPU path" maxlog = 1
+            return cpu_t2map!(maps, dist, image, opts)
+        end
+    end
+    st = last_stats()
+    st.lcurve_overflow == 0 || @warn "L-curve cache overflow in $(st.lcurve_overflow) voxels (results approximate there)"
+    opts.Silent || st.early_returns == 0 || @info "chi2/MDP early-return voxels (reference-undefined, src/lsqnonneg.jl:510-515, 708-718): $(st.early_returns)"
+    return convert(Dict{String, Any}, maps), convert(Array{Float64, 4}, dist)
+end
+
+"""
+    t2map_gpu(image::Array{Float32,4}, opts::T2mapOptions{Float64})
+
+Float32 volume in (what NIfTI files hold), Float64 arithmetic and outputs: replaces `load_image`'s
+`copyto!(Array{Float64,4}(undef, sz), data)` (src/main.jl:612-617) + `T2mapSEcorr` with half the host-to-device traffic
+(`decaes_t2map_f32`; the conversion is exact and happens on the device).
+"""
+function t2map_gpu(image::Array{Float32, 4}, opts::T2mapOptions{Float64}; ngpus::Int = 0)
+    @assert size(image) == (opts.MatrixSize..., opts.nTE)
+    maps, dist = T2Maps(opts), T2Distributions(opts)
+    copts = Ref(CT2mapOpts(opts; alpha_provided = false, ngpus))
+    decaybasis = opts.SetFlipAngle === nothing ? maps.decaybasis : nothing
+    GC.@preserve image maps dist begin
+        out = Ref(CT2mapOut(
+            pointer(maps.gdn), pointer(maps.ggm), pointer(maps.gva), pointer(maps.fnr), pointer(maps.snr), pointer(maps.alpha),
+            pointer(dist.distributions),
+            ptr_or_null(maps.resnorm), ptr_or_null(maps.decaycurve), ptr_or_null(maps.mu), ptr_or_null(maps.chi2factor),
+            ptr_or_null(decaybasis),
+            Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL),
+        ))
+        status = ccall((:decaes_t2map_f32, libdecaes_cuda), Cint,
+            (Ptr{Float32}, Ref{CT2mapOpts}, Ptr{Cvoid}, Ref{CT2mapOut}), image, copts, C_NULL, out)
+        check_status(status) || return DECAES.T2mapSEcorr(convert(Array{Float64, 4}, image), opts)
     end
     return convert(Dict{String, Any}, maps), convert(Array{Float64, 4}, dist)
 end
+
+# The reference's own generic method, reached past the GPU method below (no method piracy games: `invoke` names the
+# signature of src/T2mapSEcorr.jl:151-156 explicitly).
+cpu_t2map!(maps, dist, image, opts) =
+    invoke(DECAES.T2mapSEcorr!, Tuple{T2Maps{T}, T2Distributions{T}, Array{T, 4}, T2mapOptions{T}} where {T}, maps, dist, image, opts)
+cpu_t2part(T2distributions, opts) =
+    invoke(DECAES.T2partSEcorr, Tuple{Array{T, 4}, T2partOptions{T}} where {T}, T2distributions, opts)
+
+"""
+    pinned_array(Float64, dims...)
+
+An `Array` backed by page-locked memory from `decaes_host_alloc`: buffers allocated this way are copied to and from
+the GPUs directly; ordinary Arrays work too (the library stages them through a pinned ring, about 1 % slower on one
+GPU).  Free with `free_pinned(A)` once no Array aliases it.
+"""
+function pinned_array(::Type{T}, dims::Integer...) where {T}
+    p = ccall((:decaes_host_alloc, libdecaes_cuda), Ptr{Cvoid}, (Csize_t,), prod(dims) * sizeof(T))
+    p == C_NULL && error("decaes_host_alloc failed: $(last_error())")
+    return unsafe_wrap(Array, Ptr{T}(p), dims; own = false)
+end
+free_pinned(A::Array) = ccall((:decaes_host_free, libdecaes_cuda), Cvoid, (Ptr{Cvoid},), pointer(A))
 
 """
     t2part_gpu(T2distributions, opts)
@@ -119,7 +205,7 @@ function t2part_gpu(T2distributions::Array{Float64, 4}, opts::T2partOptions{Floa
         status = ccall((:decaes_t2part, libdecaes_cuda), Cint,
             (Ptr{Float64}, Ref{CT2partOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
             T2distributions, copts, maps.sfr, maps.sgm, maps.mfr, maps.mgm)
-        check_status(status)
+        check_status(status) || return cpu_t2part(T2distributions, opts)
     end
     return convert(Dict{String, Any}, maps)
 end
@@ -132,13 +218,20 @@ scratch and the device copy of each GPU's voxel slab.
 """
 release() = ccall((:decaes_release, libdecaes_cuda), Cvoid, ())
 
-# Route the public Float64 entry points through the GPU library (the two-line patch a maintainer
-# would apply inside DECAES itself is shown in INTEGRATION.md).
+# Routing the public Float64 entry points through the GPU library is OPT-IN: `DECAESCUDA.enable!()` adds the two
+# more specific methods below (inside DECAES itself the same thing is the two-line patch of INTEGRATION.md; adding
+# methods to another package's functions at load time would break precompilation on Julia >= 1.10).  Calls the library
+# does not accelerate - sizes beyond nT2 = 64 / nRefAngles = 64 / nTE = 72, a machine without a GPU - fall back to
+# DECAES.jl's CPU worker loop through `invoke`, so nothing the reference handles starts to throw.
 # `legacy = true` (sampled FITPACK spline for the flip angle and for the chi2 root, src/splines.jl:419-446,
-# src/lsqnonneg.jl:595-636) runs on the GPU as well; Float32 volumes keep DECAES.jl's generic CPU method.
-DECAES.T2mapSEcorr!(maps::T2Maps{Float64}, dist::T2Distributions{Float64}, image::Array{Float64, 4}, opts::T2mapOptions{Float64}) =
-    t2map_gpu!(maps, dist, image, opts)
-
-DECAES.T2partSEcorr(T2distributions::Array{Float64, 4}, opts::T2partOptions{Float64}) = t2part_gpu(T2distributions, opts)
+# src/lsqnonneg.jl:595-636) runs on the GPU as well; an all-Float32 `T2mapSEcorr(image::Array{Float32,4})` keeps
+# DECAES.jl's generic CPU method (Float32 arithmetic), `t2map_gpu(image32, opts64)` is the Float32-volume entry point.
+function enable!()
+    @eval DECAES.T2mapSEcorr!(maps::T2Maps{Float64}, dist::T2Distributions{Float64}, image::Array{Float64, 4}, opts::T2mapOptions{Float64}) =
+        DECAESCUDA.t2map_gpu!(maps, dist, image, opts)
+    @eval DECAES.T2partSEcorr(T2distributions::Array{Float64, 4}, opts::T2partOptions{Float64}) =
+        DECAESCUDA.t2part_gpu(T2distributions, opts)
+    return nothing
+end
 
 end # module
