@@ -103,7 +103,7 @@ def config_dict(args, world):
     return {"workload": workload_name(args.workload),
             "sharding": "ONE volume; rank r owns the contiguous voxel slab r (decaes_slab_bounds), no collective; T2part fused into the same kernel",
             "voxels": nvox, "voxels_per_rank": nvox // world, "l2": "inputs+outputs per step exceed L2 (no flush needed)",
-            "background_fraction": args.mask, "debug_voxels_override": bool(args.voxels)}
+            "background_fraction": args.mask, "debug_voxels_override": bool(args.voxels) or args.identical >= 0}
 
 
 def oracle_opts(orc, wl, nvox, **kw):
@@ -213,6 +213,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=131072)
     ap.add_argument("--parity-sample", type=int, default=8192)
     ap.add_argument("--mask", type=float, default=0.0, help="fraction of background voxels (first echo zeroed, ellipsoidal mask)")
+    ap.add_argument("--identical", type=int, default=-1,
+                    help="debug: every voxel is a copy of voxel K (all warps follow the same control flow; invalidates the headline)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-replicas", action="store_true")
@@ -283,6 +285,8 @@ def main():
     img = torch.empty((nTE, nloc), dtype=torch.float64, device=dev)
     pkg.mock_image_device(img.data_ptr(), nloc, nloc, v0, nTE, TE, seed=3, stream=stream)
     mask_volume(img, v0, nloc)
+    if args.identical >= 0:
+        img[:] = img[:, args.identical:args.identical + 1].clone()
     outs = alloc_dev(nloc)
     out_struct = pkg.make_out({k: v.data_ptr() for k, v in outs.items()})
     o_loc, p_loc = options(nloc)

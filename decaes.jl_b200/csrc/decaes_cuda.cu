@@ -671,9 +671,19 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   // solver variant: normal-equation active set (default) or the QR port (DECAES_SOLVER=qr, kept for A/B checks)
   const char *sv = getenv("DECAES_SOLVER");
   P.gram = !(sv && strcmp(sv, "qr") == 0);
+  // Components per pass of the shared-memory EPG: ceil(nT2 / 32) passes; among the splits with that many passes, the
+  // one whose accesses need the fewest 128-byte shared-memory wavefronts (16 doubles each) - the phase is bound by the
+  // shared-memory pipe.  nT2 = 40: 24 + 16 lanes (2 + 1 wavefronts per access) instead of 20 + 20 (2 + 2).
+  const int epg_npass = (nT2 + 31) / 32, epg_lanes_even = (nT2 + epg_npass - 1) / epg_npass;
   {
-    const int npass = (nT2 + 31) / 32;
-    P.epg_lanes = P.gram ? (nT2 + npass - 1) / npass : 32;  // the QR port keeps 32 lanes per pass
+    int best = epg_lanes_even, best_w = 1 << 30;
+    for (int lw = epg_lanes_even; lw <= 32; lw++) {
+      int w = 0;
+      for (int j0 = 0; j0 < nT2; j0 += lw) w += (std::min(lw, nT2 - j0) + 15) / 16;
+      if (w < best_w) best_w = w, best = lw;
+    }
+    P.epg_lanes = P.gram ? best : 32;  // the QR port keeps 32 lanes per pass
+    if (const char *e = getenv("DECAES_EPG_LANES")) P.epg_lanes = std::max(epg_lanes_even, std::min(32, atoi(e)));
   }
   int epg_elems = 3 * P.epg_kmax * 32;
   P.a_elems = std::max(std::max(P.rows_alloc * P.ld, P.copy_elems), epg_elems);
@@ -686,6 +696,11 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if (const char *e = getenv("DECAES_SYNC_GROUPS")) P.sync_groups = std::max(1, atoi(e));
   P.fa_warm = 4;
   if (const char *e = getenv("DECAES_FA_WARM")) P.fa_warm = atoi(e);
+  P.fa_polish = 0, P.fa_refine = 1;
+  if (const char *e = getenv("DECAES_FA_POLISH")) P.fa_polish = atoi(e);
+  if (const char *e = getenv("DECAES_FA_REFINE")) P.fa_refine = atoi(e);
+  P.lc_hints = 3;
+  if (const char *e = getenv("DECAES_LC_HINTS")) P.lc_hints = atoi(e) & 3;
   if (const char *e = getenv("DECAES_SYNC_MASK")) P.sync_mask = atoi(e);
   P.ldg = (nT2 + 1) | 1;  // one array holds the lower triangle of G and, above it, M = L^-1 (gram.cuh)
   if (P.gram) P.a_elems = nT2 * P.ldg;
@@ -746,7 +761,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
     for (int sp : {0, 1, 3}) {
       SmemLayout Ls(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, sp, P.gv_stride);
       int w = (int)std::min<size_t>(DECAES_MAX_WARPS, ((size_t)optin - 1024) / Ls.total_bytes);
-      const bool epg_ok = 3 * P.epg_kmax * (P.epg_lanes + 1) <= Ls.bd;  // the shared-memory EPG must still fit in front of the signal
+      const bool epg_ok = 3 * P.epg_kmax * P.epg_lanes <= Ls.bd;  // the shared-memory EPG must still fit in front of the signal
       if ((epg_ok && !best_epg && w >= 1) || (epg_ok == best_epg && w > best_w)) best_w = w, best_epg = epg_ok, P.spill = sp;
     }
     if (const char *e = getenv("DECAES_SPILL")) P.spill = atoi(e) & 3;
@@ -754,11 +769,12 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   SmemLayout L(nTE, nT2, P.rows_alloc, P.a_elems, P.gram, P.spill, P.gv_stride);
   plan->smem_bytes = L.total_bytes;
   // the solver block + search caches (everything in front of the voxel's signal) are idle while the basis is built
-  P.epg_smem = P.gram && 3 * P.epg_kmax * (P.epg_lanes + 1) <= L.bd;
+  if (P.gram && 3 * P.epg_kmax * P.epg_lanes > L.bd && 3 * P.epg_kmax * epg_lanes_even <= L.bd) P.epg_lanes = epg_lanes_even;
+  P.epg_smem = P.gram && 3 * P.epg_kmax * P.epg_lanes <= L.bd;
   if (const char *e = getenv("DECAES_EPG_SMEM")) P.epg_smem = P.epg_smem && atoi(e);
   P.refcon = o->RefConAngle;
-  if (P.refcon != 180.0 && !fixed && !(P.gram && 3 * P.epg_kmax * (P.epg_lanes + 1) <= L.bd))
-    return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 needs the Gram solver and %d bytes of shared EPG scratch per warp", 3 * P.epg_kmax * (P.epg_lanes + 1) * 8);
+  if (P.refcon != 180.0 && !fixed && !(P.gram && 3 * P.epg_kmax * P.epg_lanes <= L.bd))
+    return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 needs the Gram solver and %d bytes of shared EPG scratch per warp", 3 * P.epg_kmax * P.epg_lanes * 8);
   if (P.refcon != 180.0) P.epg_smem = 1;
   {
     std::lock_guard<std::mutex> lk(g_ws_mutex);
@@ -930,6 +946,7 @@ static int collect_device_stats(int dev, decaes_run_stats *st) {
     fprintf(stderr, "  mean k at append %.1f, at factor %.1f; nnls warm %.1f cold %.1f per voxel, mean final k %.1f, mean inner iters %.2f, factor fallbacks/voxel %.3f\n",
             gp[4] ? (double)gp[8] / gp[4] : 0.0, gp[5] ? (double)gp[9] / gp[5] : 0.0, gp[11] / nv, gp[12] / nv,
             gp[7] ? (double)gp[13] / gp[7] : 0.0, gp[7] ? (double)gp[14] / gp[7] : 0.0, gp[15] / nv);
+    fprintf(stderr, "  KKT-polish candidate columns per voxel %.2f\n", gp[10] / nv);
     unsigned long long kh[10];
     cudaMemcpyFromSymbol(kh, g_khist, sizeof kh);
     for (int w = 0; w < 2; w++)

@@ -77,10 +77,11 @@ __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
   unsigned hi = __reduce_or_sync(DECAES_FULL_MASK, (unsigned)(v >> 32));
   return ((unsigned long long)hi << 32) | lo;
 }
-__device__ __forceinline__ unsigned long long mask_of(const int *P, int k) {
+__device__ __noinline__ unsigned long long mask_of(const int *P, int k) {  // cold path (k <= 64: two slots per lane)
   const int lane = lane_id();
   unsigned long long m = 0ull;
-  for (int t = lane; t < k; t += 32) m |= 1ull << P[t];
+  if (lane < k) m = 1ull << P[lane];
+  if (lane + 32 < k) m |= 1ull << P[lane + 32];
   return warp_or64(m);
 }
 
@@ -129,6 +130,51 @@ __device__ __noinline__ bool gram_append(double *V, int ld, int k, int j, double
     V[GV_T2 + t] = a;
   }
   __syncwarp();
+#ifndef DECAES_OLD_APPEND
+  // |l|^2 and l'y: every lane sums the k terms in the same order (k is small; cheaper than a butterfly).  The same
+  // pass accumulates, for lane u < k, the raw entry of the new row of M, a_u = sum_{t >= u} l_t M(t,u): it does not
+  // depend on the accept test, so it overlaps with the two chains instead of forming a third stage after the rsqrt.
+  double ll = 0.0, ly = 0.0, au = 0.0;
+  const bool mine = lane < k;
+  _Pragma("unroll 4") for (int t = 0; t < k; t++) {
+    const double lt = V[GV_T2 + t];
+    double mt = 0.0;
+    if (mine && t >= lane) mt = GM_(t, lane);
+    ll = fma(lt, lt, ll);
+    ly = fma(lt, V[GV_Y + t], ly);
+    au = fma(lt, mt, au);
+  }
+  const double d2 = (T[j * ld + j] + mu2) - ll;
+  bool ok = d2 > 0.0;
+  double dinv = 0.0, ynew = 0.0;
+  if (ok) {
+    dinv = rsqrt(d2);
+    ynew = (V[GV_C + j] - ly) * dinv;
+    ok = !need_positive || ynew > 0.0;
+  }
+  if (ok) {
+    // new row of M: M(k,u) = -dinv * a_u (lane <-> column u); columns 32.. (k > 32 only) take the separate loop
+    if (mine) {
+      const double m = -dinv * au;
+      GM_(k, lane) = m;
+      V[GV_S + lane] = fma(ynew, m, V[GV_S + lane]);
+    }
+    _Pragma("unroll 1") for (int u = lane + 32; u < k; u += 32) {
+      double a = 0.0;
+      _Pragma("unroll 4") for (int t = u; t < k; t++) a = fma(V[GV_T2 + t], GM_(t, u), a);
+      const double m = -dinv * a;
+      GM_(k, u) = m;
+      V[GV_S + u] = fma(ynew, m, V[GV_S + u]);
+    }
+    if (lane == 0) {
+      GM_(k, k) = dinv;
+      V[GV_Y + k] = ynew;
+      V[GV_S + k] = ynew * dinv;
+      ((int *)(V + GV_P))[k] = j;
+    }
+    __syncwarp();
+  }
+#else
   // |l|^2 and l'y: every lane sums the k terms in the same order (k is small; cheaper than a butterfly)
   double ll = 0.0, ly = 0.0;
   _Pragma("unroll 4") for (int t = 0; t < k; t++) {
@@ -161,6 +207,7 @@ __device__ __noinline__ bool gram_append(double *V, int ld, int k, int j, double
     }
     __syncwarp();
   }
+#endif
   GP_END(0);
   return ok;
 }
@@ -236,11 +283,90 @@ __device__ __noinline__ bool gram_factor(double *V, int ld, int k, double mu2) {
   return ok;
 }
 
+#ifdef DECAES_FACTOR_SMALL
+// Factor a small active block (k <= 8) in REGISTERS: the same symmetric elimination on [K | c | I] as gram_factor,
+// with lane (i, c0) = (lane >> 2, lane & 3) holding entries q = c0 and c0 + 4 of row i (for q <= p the multipliers
+// R(i, q), beyond them what is left of K(i, q)) and a replica of y_i.  Pivot row, pivot column and y_p travel by warp
+// shuffles: no shared-memory round trips and no barriers inside the elimination (gram_factor needs two per step).
+// M, y and s = M'y are written to shared memory at the end, exactly where gram_factor leaves them.  73 % of the
+// (re)factorisations of the benchmark volumes have k <= 8 (DECAES_PROFILE histogram).
+template <int VS>
+__device__ __noinline__ bool gram_factor_small(double *V, int ld, int k, double mu2) {
+  GV_LAYOUT(VS);
+  __builtin_assume(__isShared(V));
+  const int lane = lane_id();
+  const int i = lane >> 2, c0 = lane & 3, c1 = c0 + 4;
+  double *T = V + GV_T;
+  const int *P = (const int *)(V + GV_P);
+  GP_BEGIN();
+  GP_ADD(9, k);
+  GP_HIST(1, k);
+  const bool rv = i < k, v0 = rv && c0 <= i, v1 = rv && c1 <= i;
+  const int pi = P[rv ? i : 0];
+  double e0 = 0.0, e1 = 0.0;
+  if (v0) e0 = gram_G(T, ld, pi, P[c0]) + (c0 == i ? mu2 : 0.0);
+  if (v1) e1 = gram_G(T, ld, pi, P[c1]) + (c1 == i ? mu2 : 0.0);
+  double y = rv ? V[GV_C + pi] : 0.0;
+  const int rowbase = lane & ~3;
+  bool ok = true;
+  _Pragma("unroll 1") for (int p = 0; p < k; p++) {
+    const int pc = p & 3;
+    const double v = (p >> 2) ? e1 : e0;  // for the lanes with c0 == pc: their row's entry in column p
+    const double d = __shfl_sync(DECAES_FULL_MASK, v, 4 * p + pc);       // K(p, p)
+    const double colv = __shfl_sync(DECAES_FULL_MASK, v, rowbase | pc);  // K(i, p)
+    const double a0 = __shfl_sync(DECAES_FULL_MASK, e0, 4 * p + c0);     // R(p, c0)
+    const double a1 = __shfl_sync(DECAES_FULL_MASK, e1, 4 * p + c0);     // R(p, c1)
+    const double b0 = __shfl_sync(DECAES_FULL_MASK, v, 4 * c0 + pc);     // K(c0, p)
+    const double b1 = __shfl_sync(DECAES_FULL_MASK, v, 4 * c1 + pc);     // K(c1, p)
+    const double yp = __shfl_sync(DECAES_FULL_MASK, y, 4 * p);
+    if (!(d > 0.0)) {
+      ok = false;
+      break;
+    }
+    const double f = colv * __drcp_rn(d);
+    if (rv && i > p) {
+      // row_i -= f * (row p of R | column p of K) on the entries q in [0, i] \ {p}; entry p becomes -f
+      if (v0) e0 = (c0 == p) ? -f : fma(-f, c0 < p ? a0 : b0, e0);
+      if (v1) e1 = (c1 == p) ? -f : fma(-f, c1 < p ? a1 : b1, e1);
+      y = fma(-f, yp, y);
+    }
+  }
+  if (ok) {
+    const double dii = __shfl_sync(DECAES_FULL_MASK, (i >> 2) ? e1 : e0, rowbase | (i & 3));
+    const double dinv = rsqrt(rv ? dii : 1.0);
+    e0 = (c0 == i) ? dinv : e0 * dinv;
+    e1 = (c1 == i) ? dinv : e1 * dinv;
+    y *= dinv;
+    if (v0) GM_(i, c0) = e0;
+    if (v1) GM_(i, c1) = e1;
+    if (rv && c0 == 0) V[GV_Y + i] = y;
+    // s_u = sum_{t >= u} M(t, u) y_t: one product per entry, summed over the rows (lane bits 2..4)
+    double s0 = v0 ? e0 * y : 0.0, s1 = v1 ? e1 * y : 0.0;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      s0 += __shfl_xor_sync(DECAES_FULL_MASK, s0, o);
+      s1 += __shfl_xor_sync(DECAES_FULL_MASK, s1, o);
+    }
+    if (i == 0) {
+      if (c0 < k) V[GV_S + c0] = s0;
+      if (c1 < k) V[GV_S + c1] = s1;
+    }
+  }
+  __syncwarp();
+  GP_END(1);
+  return ok;
+}
+#endif
+
 // (Re)build the factorisation of the columns listed in P[0:k).  Returns the number of columns kept.
 template <int VS>
 __device__ __noinline__ int gram_refactor(double *V, int ld, int k, double mu2) {
   GV_LAYOUT(VS);
+#ifdef DECAES_FACTOR_SMALL  // measured neutral (fewer instructions, larger instruction-cache footprint): off
+  if (k == 0 || (k <= 8 ? gram_factor_small<VS>(V, ld, k, mu2) : gram_factor<VS>(V, ld, k, mu2))) return k;
+#else
   if (k == 0 || gram_factor<VS>(V, ld, k, mu2)) return k;
+#endif
   // numerically dependent set (rare): sequential appends, dropping the offending columns
   GP_ADD(15, 1);
   int *P = (int *)(V + GV_P);
@@ -258,12 +384,13 @@ __device__ __noinline__ int gram_refactor(double *V, int ld, int k, double mu2) 
   return kk;
 }
 
-// Remove pivot position r from the factorisation (k <= 32 columns) by Givens rotations instead of a
-// refactorisation: rotating rows (i, i+1), i = r..k-2, of M pushes the mass of column r into the last
-// row; dropping that row and column r leaves the inverse Cholesky factor of the reduced block (up to
-// row signs, which neither the append formulas nor s = M'y care about).  lane <-> column u of M: a
-// rotation touches only the lane's own two entries, the rotation coefficients follow from column r
-// alone and are computed redundantly by every lane; lane r (whose column disappears) carries y.
+// Remove pivot position r from the factorisation by Givens rotations instead of a refactorisation:
+// rotating rows (i, i+1), i = r..k-2, of M pushes the mass of column r into the last row; dropping that
+// row and column r leaves the inverse Cholesky factor of the reduced block (up to row signs, which
+// neither the append formulas nor s = M'y care about).  lane <-> columns lane and lane + 32 of M (the
+// second one only when k > 32, warp-uniform): a rotation touches only the lane's own entries, the
+// rotation coefficients follow from column r alone and are computed redundantly by every lane; the lane
+// whose column disappears carries y.  Removing the LAST pivot costs nothing (no rotation).
 // The caller compacts P and recomputes s (gram_solve_s) once all removals are done.
 template <int VS>
 __device__ __noinline__ void gram_downdate(double *V, int ld, int k, int r) {
@@ -271,27 +398,39 @@ __device__ __noinline__ void gram_downdate(double *V, int ld, int k, int r) {
   __builtin_assume(__isShared(V));
   const int lane = lane_id();
   double *T = V + GV_T;
-  const int u = lane;                      // this lane's column
-  const int ud = u - (u > r ? 1 : 0);      // ... and where it ends up
-  const bool isy = (u == r);
-  double a = GM_(r, r);                    // running (i, r) entry
-  double carry = isy ? V[GV_Y + r] : (u < r ? GM_(r, u) : 0.0);
+  const bool wide = k > 32;
+  const int u0 = lane, u1 = lane + 32;          // this lane's columns
+  const int ud0 = u0 - (u0 > r ? 1 : 0), ud1 = u1 - (u1 > r ? 1 : 0);  // ... and where they end up
+  const bool isy0 = (u0 == r), isy1 = (u1 == r);
+  double a = GM_(r, r);                         // running (i, r) entry
+  double carry0 = isy0 ? V[GV_Y + r] : (u0 < r ? GM_(r, u0) : 0.0), carry1 = 0.0;
+  if (wide) carry1 = isy1 ? V[GV_Y + r] : (u1 < r ? GM_(r, u1) : 0.0);
   _Pragma("unroll 1") for (int i = r; i < k - 1; i++) {
     const double b = GM_(i + 1, r);
     const double h2 = fma(a, a, b * b);
     const double hinv = rsqrt(h2);
     const double c = b * hinv, sn = a * hinv;
     a = h2 * hinv;
-    double e = 0.0;
-    if (isy) e = V[GV_Y + i + 1];
-    else if (u < k && u <= i + 1) e = GM_(i + 1, u);
-    const double ni = c * carry - sn * e;
-    carry = fma(sn, carry, c * e);
+    double e0 = 0.0, e1 = 0.0, n1 = 0.0;
+    if (isy0) e0 = V[GV_Y + i + 1];
+    else if (u0 < k && u0 <= i + 1) e0 = GM_(i + 1, u0);
+    const double n0 = c * carry0 - sn * e0;
+    carry0 = fma(sn, carry0, c * e0);
+    if (wide) {
+      if (isy1) e1 = V[GV_Y + i + 1];
+      else if (u1 < k && u1 <= i + 1) e1 = GM_(i + 1, u1);
+      n1 = c * carry1 - sn * e1;
+      carry1 = fma(sn, carry1, c * e1);
+    }
     // one barrier per rotation: row i was last read in the previous iteration (and M(r,r) before the
     // loop); it is overwritten now (a lane writes into its left neighbour's column)
     __syncwarp();
-    if (isy) V[GV_Y + i] = ni;
-    else if (u < k && u <= i + 1) GM_(i, ud) = ni;
+    if (isy0) V[GV_Y + i] = n0;
+    else if (u0 < k && u0 <= i + 1) GM_(i, ud0) = n0;
+    if (wide) {
+      if (isy1) V[GV_Y + i] = n1;
+      else if (u1 < k && u1 <= i + 1) GM_(i, ud1) = n1;
+    }
   }
   __syncwarp();
 }
@@ -311,27 +450,26 @@ __device__ __forceinline__ void gram_solve_s(double *V, int ld, int k) {
 }
 
 // Remove pivot position imv, then any other non-positive coefficient (first found), compacting P
-// (src/NNLS.jl:735-778); the factorisation follows by Givens downdates (k <= 32) or is rebuilt.
+// (src/NNLS.jl:735-778); the factorisation follows by Givens downdates and the removed columns leave `mask`.
 // Returns the new number of active columns; s is up to date on return.
 template <int VS>
-__device__ __noinline__ int gram_remove(double *V, int ld, int k, int imv, double mu2) {
+__device__ __noinline__ int gram_remove(double *V, int ld, int k, int imv, unsigned long long &mask) {
   GV_LAYOUT(VS);
   __builtin_assume(__isShared(V));
   const int lane = lane_id();
   int *P = (int *)(V + GV_P);
-  const bool small = k <= 32;
   while (true) {
-    if (small) gram_downdate<VS>(V, ld, k, imv);
-    int pn = 0;
-    if (lane >= imv && lane < k - 1) pn = P[lane + 1];
-    if (lane == 0) V[GV_X + P[imv]] = 0.0;
+    gram_downdate<VS>(V, ld, k, imv);
+    const bool m0 = lane >= imv && lane < k - 1, m1 = lane + 32 >= imv && lane + 32 < k - 1;
+    int pn0 = 0, pn1 = 0;
+    if (m0) pn0 = P[lane + 1];
+    if (m1) pn1 = P[lane + 33];
+    const int jrem = P[imv];
+    mask &= ~(1ull << jrem);
+    if (lane == 0) V[GV_X + jrem] = 0.0;
     __syncwarp();
-    if (k > 32) {
-      if (lane == 0)
-        for (int t = imv; t < k - 1; t++) P[t] = P[t + 1];
-    } else if (lane >= imv && lane < k - 1) {
-      P[lane] = pn;
-    }
+    if (m0) P[lane] = pn0;
+    if (m1) P[lane + 32] = pn1;
     __syncwarp();
     k -= 1;
     unsigned bad = 0x7fffffffu;
@@ -341,11 +479,8 @@ __device__ __noinline__ int gram_remove(double *V, int ld, int k, int imv, doubl
     if (bad == 0x7fffffffu) break;
     imv = (int)bad;
   }
-  if (small) {
-    gram_solve_s<VS>(V, ld, k);
-    return k;
-  }
-  return gram_refactor<VS>(V, ld, k, mu2);
+  gram_solve_s<VS>(V, ld, k);
+  return k;
 }
 
 // Lawson–Hanson main loop.  cold: start from the empty set with the reference's warm dual
@@ -456,8 +591,7 @@ __device__ __noinline__ GramOut gram_nnls(double *V, int n, int ld, double mu2, 
         V[GV_X + jx] = fma(al, V[GV_S + t] - V[GV_X + jx], V[GV_X + jx]);
       }
       __syncwarp();
-      k = gram_remove<VS>(V, ld, k, imv, mu2);
-      mask = mask_of(P, k);
+      k = gram_remove<VS>(V, ld, k, imv, mask);
     }
     if (capped) {
       hit_cap = true;

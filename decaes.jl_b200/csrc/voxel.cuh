@@ -48,6 +48,9 @@ struct PipeParams {
   int sync_mask;            // which intra-round CTA barriers are active (bit 0: after flip angle, bit 1: after basis)
   int epg_smem;             // EPG at the fitted angle keeps its states in shared memory (lane <-> component)
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
+  int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too (default: only on the solves whose x is an output)
+  int fa_refine;            // iterative-refinement step on the flip-angle probes
+  int lc_hints;             // L-curve start hints: bit 0 = full column set at mu = e^2, bit 1 = flip-angle fit's set at mu = e^-8
   double angles[DECAES_MAX_ANGLES];                            // flip-angle grid (degrees)
   double logT2[DECAES_MAX_NT2], E2[DECAES_MAX_NT2];            // log(T2_j), exp(-(TE/2)/T2_j)
   double weights[DECAES_MAX_NT2];                              // sigmoid weights (has_sigmoid)
@@ -78,7 +81,7 @@ struct ScratchLayout {
 
 // per-warp shared memory layout (in doubles, then ints)
 struct SmemLayout {
-  int A, b, u, x, w, bd, sig, fit, slot_mu, slot_r2, slot_x2, slot_mask, idx, bar, total_bytes;
+  int A, b, u, x, w, bd, sig, fit, slot_mu, slot_lmu, slot_r2, slot_x2, slot_mask, idx, bar, total_bytes;
   int M, c, y, s, t1, t2, lc_pts, lc_states, slots_x, fa_u, fa_du, fa_mask;  // Gram solver only
   // spill (Gram solver): bit 0 = the cached solutions (slots_x), bit 1 = the L-curve state records live in the warp's
   // global scratch instead (one L2 round trip per solve / per L-curve step, 2.5 KB each of shared memory back)
@@ -106,6 +109,7 @@ struct SmemLayout {
     // the voxel's signal and the mbarrier must survive it
     fit = o, o += nTE;
     slot_mu = o, o += DECAES_NCACHE;
+    slot_lmu = o, o += DECAES_NCACHE;
     slot_r2 = o, o += DECAES_NCACHE;
     slot_x2 = o, o += DECAES_NCACHE;
     slot_mask = o, o += DECAES_NCACHE;
@@ -173,7 +177,8 @@ struct Warp {
   // dominate the latency of the scalar search code), global scratch for the QR port
   double *lc_pts_p, *lc_states_p, *slots_x_p, *fa_u_p, *fa_du_p;
   unsigned long long *fa_mask_p;
-  double *bd, *sig, *fit, *slot_mu, *slot_r2, *slot_x2;
+  double *bd, *sig, *fit, *slot_mu, *slot_lmu, *slot_r2, *slot_x2;
+  unsigned long long fa_mask_best;  // active set of the probed grid angle nearest to the fitted one (0 = none)
   uint64_t *bar;
   unsigned phase;
   double *g;  // global scratch of this warp
@@ -204,7 +209,8 @@ struct Warp {
       fa_u_p = gscratch + sl.fa_u, fa_du_p = gscratch + sl.fa_du, fa_mask_p = (unsigned long long *)(gscratch + sl.fa_mask);
     }
     bd = smem + L.bd, sig = nullptr, fit = smem + L.fit;
-    slot_mu = smem + L.slot_mu, slot_r2 = smem + L.slot_r2, slot_x2 = smem + L.slot_x2;
+    slot_mu = smem + L.slot_mu, slot_lmu = smem + L.slot_lmu, slot_r2 = smem + L.slot_r2, slot_x2 = smem + L.slot_x2;
+    fa_mask_best = 0ull;
     bar = (uint64_t *)(smem + L.bar);
     phase = 0;
     g = gscratch;
@@ -458,7 +464,15 @@ struct Warp {
       }
       if constexpr (!LEGACY) suggest_point(seen, x, u);
       else if (seen != seen_sugg) suggest_point_legacy(seen, x, u), seen_sugg = seen;
-      if (numeval >= maxeval || (hi - lo) <= 1) break;
+      if (numeval >= maxeval || (hi - lo) <= 1) {
+        if constexpr (GRAM) {
+          // active set of the probed node nearest to the fitted angle: warm start of the first regularised solve
+          int In = (fabs(cP.angles[lo] - x) <= fabs(cP.angles[hi] - x)) ? lo : hi;
+          if (!((seen >> In) & 1ull)) In = lo + hi - In;
+          fa_mask_best = ((seen >> In) & 1ull) ? fa_mask_p[In] : 0ull;
+        }
+        break;
+      }
     }
     return x;
   }
@@ -481,65 +495,68 @@ struct Warp {
     const double m0 = sind_0_180(alpha_deg / 2);
     const double E1 = cP.E1;
     // the three state arrays never alias: lets the compiler overlap the loads of one state with the stores of the previous one
-    // LW lanes per pass: the n components are split evenly over ceil(n/32) passes (40 -> 2 x 20), which costs the same
-    // as 32 + 8 and shrinks the scratch to 3 K LW doubles
-    const int LW = cP.epg_lanes, LS = LW + 1;  // row stride: one spare column that all idle lanes share
-    const int ls = lane < LW ? lane : LW;
-    double *const sF = S + ls, *const sB = S + K * LS + ls, *const sZ = S + 2 * K * LS + ls;
-#define ST(c, k) ((c) == 0 ? sF : (c) == 1 ? sB : sZ)[((k)-1) * LS]
+    // LW lanes per pass (PipeParams::epg_lanes).  The phase is bound by the shared-memory pipe (all warps of the CTA run
+    // it at the same time) and a 64-bit access costs one wavefront per HALF-warp that has an active lane, so the host
+    // picks the split with the fewest active half-warps (nT2 = 40: 24 + 16 lanes = 2 + 1 wavefronts per access instead
+    // of 2 + 2 for 20 + 20) and the idle lanes of a pass sit the whole recursion out (no loads, no stores).
+    const int LW = cP.epg_lanes, LS = LW;
     for (int j0 = 0; j0 < n; j0 += LW) {
-      const int j = j0 + ls;
-      const bool act = lane < LW && j < n;
-      const double E2 = act ? cP.E2[j] : 0.0;
-      const double E2h = __dmul_rn(E2, E2) / 2, E1E2 = __dmul_rn(E1, E2), E1sq = __dmul_rn(E1, E1);
-      const double a = E2h, b = __dmul_rn(E2h, cosa), c = __dmul_rn(E1E2, sina), d = __dmul_rn(E1sq, cosa);
-      const double cp = -c / 2;
-      double F, Fb, Z, C, Sd, Cp, Sp, vF, vFb, vZ;
+      const int j = j0 + lane;
+      if (lane < LW && j < n) {
+        double *const sF = S + lane, *const sB = S + K * LS + lane, *const sZ = S + 2 * K * LS + lane;
+#define ST(c, k) ((c) == 0 ? sF : (c) == 1 ? sB : sZ)[((k)-1) * LS]
+        const double E2 = cP.E2[j];
+        const double E2h = __dmul_rn(E2, E2) / 2, E1E2 = __dmul_rn(E1, E2), E1sq = __dmul_rn(E1, E1);
+        const double a = E2h, b = __dmul_rn(E2h, cosa), c = __dmul_rn(E1E2, sina), d = __dmul_rn(E1sq, cosa);
+        const double cp = -c / 2;
+        double F, Fb, Z, C, Sd, Cp, Sp, vF, vFb, vZ;
 #define UPD()                                   \
   C = __dadd_rn(F, Fb), Sd = __dsub_rn(F, Fb);  \
   Cp = __dmul_rn(a, C), Sp = __dmul_rn(b, Sd);  \
   vFb = fma(-c, Z, __dsub_rn(Cp, Sp));          \
   vF = fma(c, Z, __dadd_rn(Cp, Sp));            \
   vZ = fma(cp, Sd, __dmul_rn(d, Z))
-      double dc = __dsub_rn(a, b);
-      if (act) {
-        const double val = fabs(__dmul_rn(m0, dc));
-        pr[0 * ld + j] = val;
-        if (GRAM) pc[j * ETL] = val;
-      }
-      ST(0, 1) = __dsub_rn(a, b), ST(1, 1) = 0.0, ST(2, 1) = cp;
-      ST(0, 2) = __dadd_rn(a, b), ST(1, 2) = 0.0, ST(2, 2) = 0.0;
-      for (int i = 2; i <= ETL - 1; i++) {
-        const bool first_half = (i <= ETL / 2);
-        const int kmax = first_half ? i : ETL - i + 1;
-        F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
-        UPD();
-        if (act) {
-          const double val = fabs(__dmul_rn(m0, vFb));
-          pr[(i - 1) * ld + j] = val;
-          if (GRAM) pc[j * ETL + i - 1] = val;
+        double dc = __dsub_rn(a, b);
+        {
+          const double val = fabs(__dmul_rn(m0, dc));
+          pr[0 * ld + j] = val;
+          if (GRAM) pc[j * ETL] = val;
         }
-        ST(0, 1) = vFb, ST(2, 1) = vZ;
-        double pend = vF;
-        DECAES_PRAGMA(unroll DECAES_EPG_UNROLL) for (int k = 2; k <= kmax; k++) {
-          F = ST(0, k), Fb = ST(1, k), Z = ST(2, k);
-          ST(0, k) = pend;
+        ST(0, 1) = __dsub_rn(a, b), ST(1, 1) = 0.0, ST(2, 1) = cp;
+        ST(0, 2) = __dadd_rn(a, b), ST(1, 2) = 0.0, ST(2, 2) = 0.0;
+        for (int i = 2; i <= ETL - 1; i++) {
+          const bool first_half = (i <= ETL / 2);
+          const int kmax = first_half ? i : ETL - i + 1;
+          F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
           UPD();
-          pend = vF;
-          ST(1, k - 1) = vFb;
-          ST(2, k) = vZ;
+          {
+            const double val = fabs(__dmul_rn(m0, vFb));
+            pr[(i - 1) * ld + j] = val;
+            if (GRAM) pc[j * ETL + i - 1] = val;
+          }
+          ST(0, 1) = vFb, ST(2, 1) = vZ;
+          double pend = vF;
+          DECAES_PRAGMA(unroll DECAES_EPG_UNROLL) for (int k = 2; k <= kmax; k++) {
+            F = ST(0, k), Fb = ST(1, k), Z = ST(2, k);
+            ST(0, k) = pend;
+            UPD();
+            pend = vF;
+            ST(1, k - 1) = vFb;
+            ST(2, k) = vZ;
+          }
+          ST(0, kmax + 1) = pend;
+          if (first_half) ST(1, i) = 0.0, ST(1, i + 1) = 0.0, ST(2, i + 1) = 0.0;
         }
-        ST(0, kmax + 1) = pend;
-        if (first_half) ST(1, i) = 0.0, ST(1, i + 1) = 0.0, ST(2, i + 1) = 0.0;
+        F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
+        C = __dadd_rn(F, Fb), Sd = __dsub_rn(F, Fb);
+        dc = fma(-c, Z, fma(a, C, __dmul_rn(-b, Sd)));
+        {
+          const double val = fabs(__dmul_rn(m0, dc));
+          pr[(ETL - 1) * ld + j] = val;
+          if (GRAM) pc[j * ETL + ETL - 1] = val;
+        }
       }
-      F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
-      C = __dadd_rn(F, Fb), Sd = __dsub_rn(F, Fb);
-      dc = fma(-c, Z, fma(a, C, __dmul_rn(-b, Sd)));
-      if (act) {
-        const double val = fabs(__dmul_rn(m0, dc));
-        pr[(ETL - 1) * ld + j] = val;
-        if (GRAM) pc[j * ETL + ETL - 1] = val;
-      }
+      __syncwarp();
     }
 #undef ST
 #undef UPD
@@ -575,51 +592,52 @@ struct Warp {
     const double s2h = __dmul_rn(sh, sh), c2h = __dmul_rn(ch, ch), sin1 = __dmul_rn(__dmul_rn(2.0, sh), ch);
     const double c2hi = (1 + cosi) / 2, s2hi = 1 - c2hi;
     const double E1 = cP.E1, m0 = sh;
-    const int LW = cP.epg_lanes, LS = LW + 1;  // row stride: one spare column that all idle lanes share
-    const int ls = lane < LW ? lane : LW;
-#define ST(c, k) S[((c)*K + (k)-1) * LS + ls]
+    const int LW = cP.epg_lanes, LS = LW;  // rows of LW doubles; the idle lanes of a pass sit it out (see epg_basis)
+#define ST(c, k) S[((c)*K + (k)-1) * LS + lane]
 #define DOT3(u0, u1, u2) __dadd_rn(__dadd_rn(__dmul_rn(u0, mF), __dmul_rn(u1, mFb)), __dmul_rn(u2, mZ))
     _Pragma("unroll 1") for (int j0 = 0; j0 < n; j0 += LW) {
-      const int j = j0 + ls;
-      const bool act = lane < LW && j < n;
-      const double E2 = act ? cP.E2[j] : 0.0;
-      const double E2sq = __dmul_rn(E2, E2), E1E2 = __dmul_rn(E1, E2);
-      const double a1 = __dmul_rn(E2sq, c2h), b1 = __dmul_rn(E2sq, s2h), c1 = __dmul_rn(E1E2, sin1);
-      const double ai = __dmul_rn(E2sq, c2hi), bi = __dmul_rn(E2sq, s2hi), ci = __dmul_rn(E1E2, sini);
-      const double di = __dmul_rn(__dmul_rn(E1, E1), cosi), hci = ci / 2;
-      double mF, mFb, mZ, FM, FbM, ZM;
-      ST(0, 1) = __dmul_rn(b1, m0), ST(1, 1) = 0.0, ST(2, 1) = __dmul_rn(-c1, m0) / 2;
-      ST(0, 2) = __dmul_rn(a1, m0), ST(1, 2) = 0.0, ST(2, 2) = 0.0;
-      if (act) {
-        const double val = fabs(__dmul_rn(b1, m0));
-        pr[j] = val, pc[j * ETL] = val;
-      }
-      _Pragma("unroll 1") for (int i = 2; i <= ETL - 1; i++) {
-        const bool first_half = (i <= ETL / 2);
-        const int nproc = first_half ? i : ETL - i + 1;
-        mF = ST(0, 1), mFb = ST(1, 1), mZ = ST(2, 1);
-        FM = DOT3(ai, bi, ci), FbM = DOT3(bi, ai, -ci), ZM = DOT3(-hci, hci, di);
-        if (act) {
-          const double val = fabs(FbM);
-          pr[(i - 1) * ld + j] = val, pc[j * ETL + i - 1] = val;
+      const int j = j0 + lane;
+      if (lane < LW && j < n) {
+        const double E2 = cP.E2[j];
+        const double E2sq = __dmul_rn(E2, E2), E1E2 = __dmul_rn(E1, E2);
+        const double a1 = __dmul_rn(E2sq, c2h), b1 = __dmul_rn(E2sq, s2h), c1 = __dmul_rn(E1E2, sin1);
+        const double ai = __dmul_rn(E2sq, c2hi), bi = __dmul_rn(E2sq, s2hi), ci = __dmul_rn(E1E2, sini);
+        const double di = __dmul_rn(__dmul_rn(E1, E1), cosi), hci = ci / 2;
+        double mF, mFb, mZ, FM, FbM, ZM;
+        ST(0, 1) = __dmul_rn(b1, m0), ST(1, 1) = 0.0, ST(2, 1) = __dmul_rn(-c1, m0) / 2;
+        ST(0, 2) = __dmul_rn(a1, m0), ST(1, 2) = 0.0, ST(2, 2) = 0.0;
+        {
+          const double val = fabs(__dmul_rn(b1, m0));
+          pr[j] = val, pc[j * ETL] = val;
         }
-        ST(0, 1) = FbM, ST(2, 1) = ZM;
-        double pend = FM;
-        _Pragma("unroll 1") for (int k = 2; k <= nproc; k++) {
-          mF = ST(0, k), mFb = ST(1, k), mZ = ST(2, k);
+        _Pragma("unroll 1") for (int i = 2; i <= ETL - 1; i++) {
+          const bool first_half = (i <= ETL / 2);
+          const int nproc = first_half ? i : ETL - i + 1;
+          mF = ST(0, 1), mFb = ST(1, 1), mZ = ST(2, 1);
           FM = DOT3(ai, bi, ci), FbM = DOT3(bi, ai, -ci), ZM = DOT3(-hci, hci, di);
-          ST(0, k) = pend;
-          pend = FM;
-          ST(1, k - 1) = FbM;
-          ST(2, k) = ZM;
+          {
+            const double val = fabs(FbM);
+            pr[(i - 1) * ld + j] = val, pc[j * ETL + i - 1] = val;
+          }
+          ST(0, 1) = FbM, ST(2, 1) = ZM;
+          double pend = FM;
+          _Pragma("unroll 1") for (int k = 2; k <= nproc; k++) {
+            mF = ST(0, k), mFb = ST(1, k), mZ = ST(2, k);
+            FM = DOT3(ai, bi, ci), FbM = DOT3(bi, ai, -ci), ZM = DOT3(-hci, hci, di);
+            ST(0, k) = pend;
+            pend = FM;
+            ST(1, k - 1) = FbM;
+            ST(2, k) = ZM;
+          }
+          if (first_half) ST(0, nproc + 1) = pend, ST(1, nproc) = 0.0, ST(1, nproc + 1) = 0.0, ST(2, nproc + 1) = 0.0;
         }
-        if (first_half) ST(0, nproc + 1) = pend, ST(1, nproc) = 0.0, ST(1, nproc + 1) = 0.0, ST(2, nproc + 1) = 0.0;
+        mF = ST(0, 1), mFb = ST(1, 1), mZ = ST(2, 1);
+        {
+          const double val = fabs(DOT3(bi, ai, -ci));
+          pr[(ETL - 1) * ld + j] = val, pc[j * ETL + ETL - 1] = val;
+        }
       }
-      mF = ST(0, 1), mFb = ST(1, 1), mZ = ST(2, 1);
-      if (act) {
-        const double val = fabs(DOT3(bi, ai, -ci));
-        pr[(ETL - 1) * ld + j] = val, pc[j * ETL + ETL - 1] = val;
-      }
+      __syncwarp();
     }
 #undef ST
 #undef DOT3
@@ -652,9 +670,11 @@ struct Warp {
     if (lane < DECAES_NCACHE) slot_mu[lane] = CUDART_NAN;
     __syncwarp();
   }
-  __device__ __noinline__ void cache_solve(double mu, const double *Asrc) {
+  // lmu = log(mu) when the caller has it (NaN: computed on a miss); hint (Gram solver): 1 = start from the full
+  // column set (heavily regularised solves keep nearly every column), 2 = start from the flip-angle fit's active set
+  __device__ __noinline__ void cache_solve(double mu, const double *Asrc, double lmu = NAN, int hint = 0) {
     if constexpr (GRAM) {
-      cache_solve_gram(mu, cursrc);
+      cache_solve_gram(mu, cursrc, lmu, hint);
       return;
     }
     int hit = -1, firstnan = -1;
@@ -732,13 +752,13 @@ struct Warp {
   }
 
   // cached evaluation of P(t) = (log ||Ax-b||^2, log ||x||^2); returns the point-cache index
-  __device__ __noinline__ int lc_eval(double t, int &npts, const double *Asrc) {
+  __device__ __noinline__ int lc_eval(double t, int &npts, const double *Asrc, int hint = 0) {
     const int lane = this->lane;
     VIEWG(double, lc_pts_p);
     double *pts = lc_pts_p;
     int i = lc_find(t, npts);
     if (i != 0x7fffffff) return i;
-    cache_solve(dexp(t), Asrc);
+    cache_solve(dexp(t), Asrc, t, hint);
     double xi = dlog(cur_resnorm_sq()), eta = dlog(cur_seminorm_sq());
     i = npts;
     if (npts < DECAES_LC_MAX) {
@@ -838,7 +858,9 @@ struct Warp {
     sx[0] = -8.0, sx[3] = 2.0;
     sx[1] = __dadd_rn(__dmul_rn(phi, sx[0]), sx[3]) / (phi + 1);
     sx[2] = sx[0] + (sx[3] - sx[1]);
-    for (int q = 0; q < 4; q++) si[q] = lc_eval(sx[q], npts, Asrc);
+    // first point (mu = e^-8: practically the unregularised problem) starts from the flip-angle fit's active set,
+    // the last one (mu = e^2) from the full column set
+    for (int q = 0; q < 4; q++) si[q] = lc_eval(sx[q], npts, Asrc, q == 0 ? (cP.lc_hints & 2) : (q == 3 ? (cP.lc_hints & 1) : 0));
     const double tlx = pts[4 * si[0] + 1], tly = pts[4 * si[0] + 2], brx = pts[4 * si[3] + 1], bry = pts[4 * si[3] + 2];
     lc_update_curvature(sx, si, npts, tlx, tly, brx, bry, Ctol);
     int iter = 0;
@@ -890,7 +912,7 @@ struct Warp {
   // ---- Brent root / bracket (src/optimization.jl:71-128, 177-219) on f(log mu) ----
   // mode 0: chi2 relative error (src/lsqnonneg.jl:374-385); mode 1: res^2 - delta^2 (:723-726)
   __device__ double root_fun(double logmu, double target, int mode, const double *Asrc) {
-    cache_solve(exp(logmu), Asrc);
+    cache_solve(exp(logmu), Asrc, logmu);
     double r2 = cur_resnorm_sq();
     return mode == 0 ? (r2 - target) / target : r2 - target;
   }
@@ -1056,7 +1078,7 @@ struct Warp {
   __device__ __noinline__ double gcv_fun(double logmu, const double *Asrc) {  // log(max(gcv, eps^2/m))  :1150-1154, 1213-1229
     const int m = cP.nTE, n = cP.nT2;
     double mu = exp(logmu);
-    cache_solve(mu, Asrc);
+    cache_solve(mu, Asrc, logmu);
     double r2 = cur_resnorm_sq();
     double dof = (double)((m - n) > 0 ? (m - n) : 0);
     double l2 = __dmul_rn(mu, mu);
@@ -1134,7 +1156,7 @@ struct Warp {
     // lane <-> columns lane and lane + 32: both advance together, 16 loads in flight (the matrix lives in L2)
     const double *c0 = Arm + (lane < n ? lane : 0), *c1 = Arm + (lane + 32 < n ? lane + 32 : 0);
     double a0 = 0.0, a1 = 0.0;
-    _Pragma("unroll 8") for (int i = 0; i < nTE; i++) {
+    _Pragma("unroll 4") for (int i = 0; i < nTE; i++) {
       const double bi = bd[i];
       a0 = fma(c0[i * ld], bi, a0), a1 = fma(c1[i * ld], bi, a1);
     }
@@ -1155,7 +1177,7 @@ struct Warp {
     // trip serves up to 12 loads per lane (A lives in L2; the loop is latency bound)
     const int i0 = lane < nTE ? lane : 0, i1 = lane + 32 < nTE ? lane + 32 : i0, i2 = lane + 64 < nTE ? lane + 64 : i0;
     double r0 = bd[i0], r1 = bd[i1], r2 = bd[i2];
-    _Pragma("unroll 4") for (int t = 0; t < k; t++) {
+    _Pragma("unroll 2") for (int t = 0; t < k; t++) {
       const double *col = Acm + gws.P[t] * nTE;
       const double st = gws.s[t];
       r0 = fma(-col[i0], st, r0), r1 = fma(-col[i1], st, r1), r2 = fma(-col[i2], st, r2);
@@ -1220,9 +1242,10 @@ struct Warp {
 
   // Explicit duals of the columns whose normal-equation dual (left in gws.w by gram_nnls) is not clearly negative:
   // w_j = A_j' r with r = b - A_P s in `fit`.  Returns the column with the largest positive explicit dual (first on
-  // ties, like largest_positive_dual, src/NNLS.jl:541-554) or -1.  "Clearly negative" = below -1e-6 max|c|: four orders
-  // of magnitude above the noise the normal-equation dual was seen to carry.  lane <-> echo, up to four columns per
-  // L2 round trip, butterfly sums interleaved for instruction-level parallelism.
+  // ties, like largest_positive_dual, src/NNLS.jl:541-554) or -1.  "Clearly negative" = below -1e-6 max|c| (the
+  // maximum is taken on the upper halves of the doubles, one REDUX: the threshold is a screening heuristic, four
+  // orders of magnitude above the noise the normal-equation dual was seen to carry).  lane <-> echo; two candidate
+  // columns per L2 round trip.  Written for size: almost every call finds zero to two candidates.
   __device__ __noinline__ int kkt_pick(const double *Acm, unsigned long long excl) {
     GL(Acm);
     const int lane = this->lane;
@@ -1231,32 +1254,28 @@ struct Warp {
     VIEW_GWS();
     const int nTE = cP.nTE, n = cP.nT2;
     const int j0 = lane < n ? lane : 0, j1 = lane + 32 < n ? lane + 32 : 0;
-    const double tau = -1e-6 * warp_max(fmax(lane < n ? fabs(cvec[j0]) : 0.0, lane + 32 < n ? fabs(cvec[j1]) : 0.0));
+    const double cm = fmax(lane < n ? fabs(cvec[j0]) : 0.0, lane + 32 < n ? fabs(cvec[j1]) : 0.0);
+    const unsigned hi = __reduce_max_sync(DECAES_FULL_MASK, (unsigned)__double2hiint(cm));
+    const double tau = -1e-6 * __hiloint2double((int)hi, 0);
     const unsigned c0 = __ballot_sync(DECAES_FULL_MASK, lane < n && !((excl >> j0) & 1ull) && gws.w[j0] > tau);
     const unsigned c1 = __ballot_sync(DECAES_FULL_MASK, lane + 32 < n && !((excl >> j1) & 1ull) && gws.w[j1] > tau);
     unsigned long long cand = ((unsigned long long)c1 << 32) | c0;
+    GP_ADD(10, __popcll(cand));
     const int i0 = lane < nTE ? lane : 0, i1 = lane + 32 < nTE ? lane + 32 : i0, i2 = lane + 64 < nTE ? lane + 64 : i0;
     const double r0 = lane < nTE ? fit[i0] : 0.0, r1 = lane + 32 < nTE ? fit[i1] : 0.0, r2 = lane + 64 < nTE ? fit[i2] : 0.0;
     double best = 0.0;
     int bj = -1;
     _Pragma("unroll 1") while (cand) {
-      int jc[4];
-      double a[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        jc[q] = cand ? __ffsll((long long)cand) - 1 : -1;
-        if (cand) cand &= cand - 1;
-        const double *col = Acm + (jc[q] >= 0 ? jc[q] : 0) * nTE;
-        a[q] = fma(col[i0], r0, fma(col[i1], r1, __dmul_rn(col[i2], r2)));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) a[q] += __shfl_xor_sync(DECAES_FULL_MASK, a[q], o);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        if (jc[q] >= 0 && a[q] > best) best = a[q], bj = jc[q];
+      const int ja = __ffsll((long long)cand) - 1;
+      cand &= cand - 1;
+      const int jb = cand ? __ffsll((long long)cand) - 1 : ja;
+      cand &= cand - 1;  // (0 & -1 = 0)
+      const double *ca = Acm + ja * nTE, *cb = Acm + jb * nTE;
+      double a = fma(ca[i0], r0, fma(ca[i1], r1, __dmul_rn(ca[i2], r2)));
+      double b = fma(cb[i0], r0, fma(cb[i1], r1, __dmul_rn(cb[i2], r2)));
+      a = warp_sum(a), b = warp_sum(b);
+      if (a > best) best = a, bj = ja;
+      if (b > best) best = b, bj = jb;
     }
     return bj;
   }
@@ -1265,7 +1284,8 @@ struct Warp {
   // returns ||A x - b||^2 (explicit) and leaves r in `fit`, x in gws.x, the active set in gws.cP.
   // `warm_mask` != 0: start from that active set instead (flip-angle probes only: the loss and its
   // gradient depend on the minimiser, which is unique, not on the pivoting path).
-  __device__ __noinline__ double gram_solve_unreg(const Src &src, GramOut &o, unsigned long long warm_mask = 0ull) {
+  __device__ __noinline__ double gram_solve_unreg(const Src &src, GramOut &o, unsigned long long warm_mask = 0ull, bool refine = true,
+                                                  bool polish = true) {
     const int lane = this->lane;
     VIEW(double, V);
     VIEW_GWS();
@@ -1288,7 +1308,7 @@ struct Warp {
     PROF_BEGIN(2);
     double r2 = gram_residual(src.Acm, o.k);
     PROF_END(2);
-    if (o.k > 0) {
+    if (o.k > 0 && refine) {
       PROF_BEGIN(3);
       gram_refine(src.Acm, o.k, 0.0);
       PROF_END(3);
@@ -1296,6 +1316,7 @@ struct Warp {
       r2 = gram_residual(src.Acm, o.k);
       PROF_END(2);
     }
+    if (!polish) return r2;
     // KKT polish.  The active-set decisions above were taken on normal-equation quantities: the dual w = c - G_P s
     // carries ~cond(A_P)^2 eps of noise (1e-10 on long-T2 pools), so a column whose true dual is a small positive
     // number can be left out (or a coefficient that should be clamped kept in) - a slightly worse stationary point
@@ -1362,7 +1383,9 @@ struct Warp {
       if (abs(kang - jn) <= cP.fa_warm) warm = fa_mask_p[jn];
     }
     GramOut o;
-    u = gram_solve_unreg(src, o, warm);
+    // The probes only feed the loss and its slope to the surrogate: a column with a dual of +1e-10 left out of the
+    // active set moves neither beyond 1e-10, so the KKT polish is reserved for the solves whose x is an output.
+    u = gram_solve_unreg(src, o, warm, cP.fa_refine != 0, cP.fa_polish != 0);
     if (lane == 0) fa_mask_p[kang] = o.mask;
     const double *dAk = cP.dbasis_cm + (size_t)kang * nTE * n;
     GL(dAk);
@@ -1505,10 +1528,11 @@ struct Warp {
     gram_rhs(Arm);
   }
 
-  // solve!(cache, mu) for the Gram solver: exact-mu hit, else warm-start from the nearest cached mu
-  __device__ __noinline__ void cache_solve_gram(double mu, const Src &src) {
+  // solve!(cache, mu) for the Gram solver: exact-mu hit, else warm-start from the nearest cached mu (lane <-> slot)
+  __device__ __noinline__ void cache_solve_gram(double mu, const Src &src, double lmu, int hint) {
     const int lane = this->lane;
     VIEW(double, slot_mu);
+    VIEW(double, slot_lmu);
     VIEW(double, slot_r2);
     VIEW(double, slot_x2);
     VIEW(unsigned long long, slot_mask);
@@ -1516,34 +1540,42 @@ struct Warp {
     VIEW(double, V);
     VIEW_GWS();
     const int n = cP.nT2;
-    int hit = -1, firstnan = -1, nearest = -1;
-    double dbest = CUDART_INF;
-    _Pragma("unroll 1") for (int i = 0; i < DECAES_NCACHE; i++) {
-      double mui = slot_mu[i];
-      if (isnan(mui)) {
-        if (firstnan < 0) firstnan = i;
-      } else if (mu == mui) {
-        hit = i;
-        break;
-      } else {
-        double dd = mu > mui ? ddiv(mu, mui) : ddiv(mui, mu);  // monotone in |log mu - log mui|
-        if (dd < dbest && slot_mask[i] != 0ull) dbest = dd, nearest = i;
-      }
-    }
-    if (hit >= 0) {
-      cur_slot = hit;
+    const bool isl = lane < DECAES_NCACHE;
+    const double mui = isl ? slot_mu[lane] : 0.0;
+    const unsigned hitm = __ballot_sync(DECAES_FULL_MASK, isl && mu == mui);  // NaN (empty slot) never compares equal
+    if (hitm) {
+      cur_slot = __ffs(hitm) - 1;
       return;
     }
-    cur_slot = (firstnan >= 0) ? firstnan : (cur_slot + 1) % DECAES_NCACHE;
+    const unsigned nanm = __ballot_sync(DECAES_FULL_MASK, isl && isnan(mui));
+    cur_slot = nanm ? __ffs(nanm) - 1 : (cur_slot + 1) % DECAES_NCACHE;
     const double mu2 = __dmul_rn(mu, mu);
-    GramOut o;
-    if (nearest >= 0) {
-      const double *sx = slots_x_p + nearest * n;
-      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = sx[j];
-      __syncwarp();
+    if (isnan(lmu)) lmu = dlog(mu);
+    unsigned long long wmask = 0ull;
+    if (hint == 1) {
+      wmask = n >= 64 ? ~0ull : (1ull << n) - 1ull;
+    } else if (hint == 2) {
+      wmask = fa_mask_best;
     }
+    if (wmask) {
+      // a feasible interior point on the hinted set: only the final minimiser (unique for mu > 0) matters
+      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = ((wmask >> j) & 1ull) ? 1.0 : 0.0;
+      __syncwarp();
+    } else {
+      // nearest cached mu in log distance (first slot on ties) that has a non-empty active set
+      unsigned long long key = ~0ull, best;
+      if (isl && !isnan(mui) && slot_mask[lane] != 0ull) key = (unsigned long long)__double_as_longlong(fabs(lmu - slot_lmu[lane]));
+      const int nearest = warp_argmin_bits(key, lane, best);
+      if (best != ~0ull) {
+        const double *sx = slots_x_p + nearest * n;
+        _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = sx[j];
+        wmask = slot_mask[nearest];
+        __syncwarp();
+      }
+    }
+    GramOut o;
     PROF_BEGIN(9);
-    o = gram_nnls<VS>(V, n, cP.ldg, mu2, n, nearest >= 0, nearest >= 0 ? slot_mask[nearest] : 0ull);
+    o = gram_nnls<VS>(V, n, cP.ldg, mu2, n, wmask != 0ull, wmask);
     n_itercap += o.capped;
 #ifdef DECAES_PROFILE
     if (lane == 0) {
@@ -1568,7 +1600,7 @@ struct Warp {
     double *sx = slots_x_p + cur_slot * n;
     _Pragma("unroll 1") for (int j = lane; j < n; j += 32) sx[j] = gws.x[j];
     if (lane == 0)
-      slot_mu[cur_slot] = mu, slot_r2[cur_slot] = r2, slot_x2[cur_slot] = o.xnorm_sq, slot_mask[cur_slot] = o.mask;
+      slot_mu[cur_slot] = mu, slot_lmu[cur_slot] = lmu, slot_r2[cur_slot] = r2, slot_x2[cur_slot] = o.xnorm_sq, slot_mask[cur_slot] = o.mask;
     __syncwarp();
   }
 
@@ -1586,6 +1618,7 @@ struct Warp {
     const int nTE = cP.nTE;
     v_cur = v;
     nunreg_voxel = 0;
+    fa_mask_best = 0ull;
     double mx = 0.0;
     _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
       double bi = __ldg(signal + (long long)i * cP.stride);
@@ -1643,7 +1676,7 @@ struct Warp {
         cache_reset();
         double logmu = lcurve_corner(Asrc);
         mu = dexp(logmu);
-        cache_solve(mu, Asrc);
+        cache_solve(mu, Asrc, logmu);
         src_kind = 1;
         if (want_chi2) {  // the unregularised solve only feeds chi2factor
           double r2 = cur_resnorm_sq();
@@ -1656,7 +1689,7 @@ struct Warp {
         cache_reset();
         double logmu = gcv_minimize(Asrc);
         mu = exp(logmu);
-        cache_solve(mu, Asrc);
+        cache_solve(mu, Asrc, logmu);
         src_kind = 1;
         if (want_chi2) {
           double r2 = cur_resnorm_sq();
@@ -1679,7 +1712,7 @@ struct Warp {
           double sigma = cP.NoiseLevel / max_signal;
           double delta = __dmul_rn(sqrt((double)nTE), sigma);
           double acc = 0.0;
-          for (int i = lane; i < nTE; i += 32) acc = fma(bd[i], bd[i], acc);
+          _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) acc = fma(bd[i], bd[i], acc);
           double res2_max = warp_sum(acc);
           target = __dmul_rn(delta, delta), ftol = 1e-3 * target, mode = 1;
           if (delta <= sqrt(res2_min)) {
@@ -1716,7 +1749,7 @@ struct Warp {
           if (isfinite(ff)) {
             mu = exp(xf);
             double res2_final = (mode == 0) ? __dmul_rn(target, 1 + ff) : target + ff;
-            cache_solve(mu, Asrc);
+            cache_solve(mu, Asrc, xf);
             chi2 = res2_final / res2_min;
             src_kind = 1;
           } else {
@@ -1731,7 +1764,7 @@ struct Warp {
     double *xs = ws.w;  // dual no longer needed
     {
       const double *sx = slots_x_p + cur_slot * n;
-      for (int j = lane; j < n; j += 32) {
+      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
         double xv = (src_kind == 0) ? ws.x[j] : (src_kind == 1 ? sx[j] : 0.0);
         xs[j] = __dmul_rn(xv, max_signal);
       }
@@ -1742,9 +1775,9 @@ struct Warp {
     double *resv = GRAM ? (lc_pts_p) : ws.u;
     if constexpr (GRAM) {
       const double *Acm = cursrc.Acm;
-      for (int i = lane; i < nTE; i += 32) {
+      _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
         double s0 = 0.0;
-        for (int j = 0; j < n; j++) {
+        _Pragma("unroll 1") for (int j = 0; j < n; j++) {
           double xj = xs[j];
           if (xj != 0.0) s0 = fma(Acm[j * nTE + i], xj, s0);
         }
@@ -1756,10 +1789,10 @@ struct Warp {
       }
     } else {
       stage_matrix(Asrc);  // pristine basis back into shared memory for fit = A x
-      for (int i = lane; i < nTE; i += 32) {
+      _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
         const double *row = ws.A + i * cP.ld;
         double s0 = 0.0;
-        for (int j = 0; j < n; j++) s0 = fma(row[j], xs[j], s0);
+        _Pragma("unroll 1") for (int j = 0; j < n; j++) s0 = fma(row[j], xs[j], s0);
         fit[i] = s0;
         double res = s0 - __dmul_rn(bd[i], max_signal);
         resv[i] = res;
@@ -1771,17 +1804,17 @@ struct Warp {
     r2 = warp_sum(r2);
     double mean = warp_sum(rs) / nTE;
     double var = 0.0;
-    for (int i = lane; i < nTE; i += 32) {
+    _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) {
       double dlt = resv[i] - mean;
       var = fma(dlt, dlt, var);
     }
     var = warp_sum(var);
     double S = 0.0, dotl = 0.0;
-    for (int j = lane; j < n; j += 32) S += xs[j], dotl = fma(xs[j], cP.logT2[j], dotl);
+    _Pragma("unroll 1") for (int j = lane; j < n; j += 32) S += xs[j], dotl = fma(xs[j], cP.logT2[j], dotl);
     S = warp_sum(S), dotl = warp_sum(dotl);
     double log_ggm = dotl / S;
     double l1p = 0.0;
-    for (int j = lane; j < n; j += 32) {
+    _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
       double dlt = cP.logT2[j] - log_ggm;
       l1p = fma(__dmul_rn(dlt, dlt), xs[j], l1p);
     }
@@ -1797,15 +1830,15 @@ struct Warp {
       if (cP.mu && cP.chi2factor) cP.mu[v] = mu, cP.chi2factor[v] = chi2;
       if (cP.resnorm) cP.resnorm[v] = sqrt(r2);
     }
-    for (int j = lane; j < n; j += 32) cP.dist[v + (long long)j * cP.stride] = xs[j];
+    _Pragma("unroll 1") for (int j = lane; j < n; j += 32) cP.dist[v + (long long)j * cP.stride] = xs[j];
     if (cP.decaycurve)
-      for (int i = lane; i < nTE; i += 32) cP.decaycurve[v + (long long)i * cP.stride] = fit[i];
+      _Pragma("unroll 1") for (int i = lane; i < nTE; i += 32) cP.decaycurve[v + (long long)i * cP.stride] = fit[i];
 
     // fused T2part epilogue  src/T2partSEcorr.jl:95-138
     if (cP.has_part) {
       bool isn = false;
       double Ssp = 0, Smp = 0, dsp = 0, dmp = 0, dw = 0;
-      for (int j = lane; j < n; j += 32) {
+      _Pragma("unroll 1") for (int j = lane; j < n; j += 32) {
         double dj = xs[j];
         isn |= isnan(dj);
         if (j >= cP.sp_lo && j <= cP.sp_hi) dsp += __dmul_rn(dj, cP.logT2[j]), Ssp += dj;

@@ -67,3 +67,11 @@ def compare(ref, got, scalars=("alpha", "sfr", "ggm"), extra=("gdn", "gva", "fnr
         rep["out_of_tolerance_same_mu"] = rep["voxels_out_of_tolerance"]
         rep["frac_out_of_tolerance_same_mu"] = rep["frac_out_of_tolerance"]
     return rep
+
+
+def flip_bound(own, n):
+    """GPU mu flips allowed on n voxels when two CPU builds of the oracle flip a fraction `own` of the same voxels: the
+    same rate + 15 % + three sigmas of binomial sampling noise (the flips of two faithful implementations are
+    independent draws from the same chaotic process, tests/test_oracle_sensitivity.py)."""
+    import math
+    return 1.15 * own + 3.0 * math.sqrt(max(own, 1.0 / n) * (1 - own) / n)

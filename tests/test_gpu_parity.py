@@ -200,9 +200,9 @@ def test_odd_sizes(pkg, orc, nTE, nT2):
             alt, _ = orc.t2map(img, o, L=orc.lib_variant("simd"))
             own = parity.compare(ref, alt)["mu_flip_frac"]
         assert rep["nan_mismatch"] == 0
-        # north_star bounds: same mu => within tolerance; flips no more frequent than between two CPU builds (64 voxels:
-        # one extra voxel of slack)
-        assert rep["out_of_tolerance_same_mu"] <= 1 and rep["mu_flip_frac"] <= own + 2.0 / nvox, (Reg, own, rep)
+        # north_star bounds: same mu => within tolerance; flips no more frequent than between two CPU builds of the
+        # oracle on the same 256 voxels (plus the sampling noise of so small a sample, parity.flip_bound)
+        assert rep["out_of_tolerance_same_mu"] <= 1 and rep["mu_flip_frac"] <= parity.flip_bound(own, nvox), (Reg, own, rep)
 
 
 def test_t2part_standalone_bit_exact_structure(pkg, orc):

@@ -64,9 +64,7 @@ CASES = [("snr15", TWO, 15.0, 40), ("snr25", TWO, 25.0, 40), ("snr40", TWO, 40.0
          ("nT2_60", TWO, 60.0, 60)]
 
 
-def flip_bound(own, n):
-    """GPU flips allowed: the two-CPU-builds rate on the same voxels + 15 % + three sigmas of sampling noise."""
-    return 1.15 * own + 3.0 * math.sqrt(max(own, 1.0 / n) * (1 - own) / n)
+flip_bound = parity.flip_bound
 
 
 @pytest.mark.parametrize("name,pools,SNR,nT2", CASES, ids=[c[0] for c in CASES])
