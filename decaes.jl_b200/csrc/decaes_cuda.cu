@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
     if (P.sync_mask & 4) group_sync();
     long long t1 = clock64();
     if (have) W.phase_flip_angle(v, signal);
+    else if (P.step_sync & 1) cta_drain();  // warps without a voxel take part in the votes
     long long t2 = clock64();
     if (!group_or(have)) break;  // every warp of the group is out of work
     long long t3 = clock64();
@@ -298,6 +299,8 @@ __global__ void __launch_bounds__(DECAES_MAX_WARPS * 32, 1) voxel_pipeline_kerne
     if (have) {
       W.phase_solve_and_save();
       processed++;
+    } else if (P.step_sync & 14) {
+      cta_drain();
     }
     long long t6 = clock64();
     cyc[0] += (t1 - t0) + (t3 - t2) + (t5 - t4), cyc[1] += t2 - t1, cyc[2] += t4 - t3, cyc[3] += t6 - t5;
@@ -696,11 +699,18 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if (const char *e = getenv("DECAES_SYNC_GROUPS")) P.sync_groups = std::max(1, atoi(e));
   P.fa_warm = 4;
   if (const char *e = getenv("DECAES_FA_WARM")) P.fa_warm = atoi(e);
-  P.fa_polish = 0, P.fa_refine = 1;
+  P.fa_polish = 1, P.fa_refine = 1;
   if (const char *e = getenv("DECAES_FA_POLISH")) P.fa_polish = atoi(e);
+  P.kkt_tau = 1e-8;  // two orders of magnitude above the noise of the normal-equation duals (1e-6: three candidates per solve instead of one)
+  if (const char *e = getenv("DECAES_KKT_TAU")) P.kkt_tau = atof(e);
   if (const char *e = getenv("DECAES_FA_REFINE")) P.fa_refine = atoi(e);
-  P.lc_hints = 3;
-  if (const char *e = getenv("DECAES_LC_HINTS")) P.lc_hints = atoi(e) & 3;
+  P.lc_hints = 7;  // bit 2: the full-set start is a direct Cholesky solve (gram_dense_solve)
+  if (const char *e = getenv("DECAES_LC_HINTS")) P.lc_hints = atoi(e) & 7;
+  // In-phase votes (voxel.cuh: cta_or): flip-angle probes and L-curve steps are uniform enough that keeping the warps
+  // in step pays (cfg3: +20 %, cfg1: +13 %); the four initial L-curve points and the Brent searches vary too much between
+  // voxels (-1 % / -6 %).  With few warps per SM (nT2 = 60: six) there is little instruction-cache pressure to relieve
+  // and the votes only cost (cfg4 / cfg5: -2 to -3 %): decided below, once the CTA shape is known.
+  P.step_sync = 3;
   if (const char *e = getenv("DECAES_SYNC_MASK")) P.sync_mask = atoi(e);
   P.ldg = (nT2 + 1) | 1;  // one array holds the lower triangle of G and, above it, M = L^-1 (gram.cuh)
   if (P.gram) P.a_elems = nT2 * P.ldg;
@@ -772,6 +782,8 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if (P.gram && 3 * P.epg_kmax * P.epg_lanes > L.bd && 3 * P.epg_kmax * epg_lanes_even <= L.bd) P.epg_lanes = epg_lanes_even;
   P.epg_smem = P.gram && 3 * P.epg_kmax * P.epg_lanes <= L.bd;
   if (const char *e = getenv("DECAES_EPG_SMEM")) P.epg_smem = P.epg_smem && atoi(e);
+  P.gcv_smem = P.gram && o->reg == DECAES_REG_GCV && nTE * nT2 <= L.bd && std::min(nTE, nT2) <= 64;
+  if (const char *e = getenv("DECAES_GCV_SMEM")) P.gcv_smem = P.gcv_smem && atoi(e);
   P.refcon = o->RefConAngle;
   if (P.refcon != 180.0 && !fixed && !(P.gram && 3 * P.epg_kmax * P.epg_lanes <= L.bd))
     return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 needs the Gram solver and %d bytes of shared EPG scratch per warp", 3 * P.epg_kmax * P.epg_lanes * 8);
@@ -800,6 +812,11 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if (const char *e = getenv("DECAES_WARPS_PER_CTA")) wpc = std::max(1, std::min(wpc, atoi(e)));
   if (wpc < 1) return fail(DECAES_EUNSUPPORTED, "not enough shared memory for one warp");
   P.warps_per_cta = wpc, P.smem_per_warp = plan->smem_bytes;
+  if (wpc < 9) P.step_sync = 0;
+  if (const char *e = getenv("DECAES_STEP_SYNC")) P.step_sync = atoi(e) & 15;
+  if (fixed || o->alpha_provided) P.step_sync &= ~1;
+  if (o->reg != DECAES_REG_LCURVE) P.step_sync &= ~6;
+  if (o->reg == DECAES_REG_LCURVE || o->reg == DECAES_REG_NONE) P.step_sync &= ~8;
   plan->warps_per_cta = wpc;
   plan->cta_smem = wpc * plan->smem_bytes;
   CUDA_TRY(cudaFuncSetAttribute(pipeline_kernel_for(P), cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));

@@ -283,7 +283,7 @@ __device__ __noinline__ bool gram_factor(double *V, int ld, int k, double mu2) {
   return ok;
 }
 
-#ifdef DECAES_FACTOR_SMALL
+#ifndef DECAES_NO_FACTOR_SMALL
 // Factor a small active block (k <= 8) in REGISTERS: the same symmetric elimination on [K | c | I] as gram_factor,
 // with lane (i, c0) = (lane >> 2, lane & 3) holding entries q = c0 and c0 + 4 of row i (for q <= p the multipliers
 // R(i, q), beyond them what is left of K(i, q)) and a replica of y_i.  Pivot row, pivot column and y_p travel by warp
@@ -362,7 +362,7 @@ __device__ __noinline__ bool gram_factor_small(double *V, int ld, int k, double 
 template <int VS>
 __device__ __noinline__ int gram_refactor(double *V, int ld, int k, double mu2) {
   GV_LAYOUT(VS);
-#ifdef DECAES_FACTOR_SMALL  // measured neutral (fewer instructions, larger instruction-cache footprint): off
+#ifndef DECAES_NO_FACTOR_SMALL
   if (k == 0 || (k <= 8 ? gram_factor_small<VS>(V, ld, k, mu2) : gram_factor<VS>(V, ld, k, mu2))) return k;
 #else
   if (k == 0 || gram_factor<VS>(V, ld, k, mu2)) return k;
@@ -480,6 +480,109 @@ __device__ __noinline__ int gram_remove(double *V, int ld, int k, int imv, unsig
     imv = (int)bad;
   }
   gram_solve_s<VS>(V, ld, k);
+  return k;
+}
+
+// Heavily regularised solves (mu = e^2, the right end of the L-curve) keep nearly every column: instead of ~25 pivots
+// one at a time, solve on the full set F directly and drop what comes out non-positive.  Left-looking Cholesky of
+// K = G_FF + mu2 I in M's storage (L(t,u) where M(t,u) would be, 1/L(p,p) on the diagonal), the right-hand side riding
+// along as an extra row (y = L^-1 c_F in GV_Y); lane <-> row, two rows per lane while more than 32 are left.  Back
+// substitution in registers.  Positions with s <= 0 leave F and the factorisation resumes at the first of them:
+// dropping the LAST pivots (the long-T2 columns, which is what happens) costs only the back substitution.  The result
+// is accepted when the duals of the excluded columns are all <= 0 - a KKT point of a strictly convex problem is its
+// minimiser; otherwise (or after 4 rounds, or on a non-positive pivot) the caller falls back to the active-set
+// iteration, warm-started from what is left of F.
+// Returns k (P[0:k), s in GV_S, x in GV_X, `mask` = F, xnorm_sq) or -1.
+template <int VS>
+__device__ __noinline__ int gram_dense_solve(double *V, int n, int ld, double mu2, unsigned long long &mask, double &xnorm_sq) {
+  GV_LAYOUT(VS);
+  __builtin_assume(__isShared(V));
+  const int lane = lane_id();
+  double *T = V + GV_T;
+  int *P = (int *)(V + GV_P);
+  const unsigned long long full = mask;
+  int k = __popcll(mask), p0 = 0;
+  double s0 = 0.0, s1 = 0.0;
+  _Pragma("unroll 1") for (int round = 0;; round++) {
+    if (round == 4 || k == 0) return -1;
+    // pivot list in ascending column order (positions below p0 are unchanged)
+    if (lane < n && ((mask >> lane) & 1ull)) P[__popcll(mask & ((1ull << lane) - 1ull))] = lane;
+    if (lane + 32 < n && ((mask >> (lane + 32)) & 1ull)) P[__popcll(mask & ((1ull << (lane + 32)) - 1ull))] = lane + 32;
+    __syncwarp();
+    _Pragma("unroll 1") for (int p = p0; p < k; p++) {
+      const int jp = P[p];
+      const int i0 = p + lane, i1 = i0 + 32;  // rows of this lane; row k is the right-hand side
+      double a0 = 0.0, a1 = 0.0;
+      const double *r0 = V + GV_Y, *r1 = V + GV_Y;
+      int st0 = 1, st1 = 1;
+      if (i0 < k) a0 = gram_G(T, ld, P[i0], jp), r0 = T + i0 + 1, st0 = ld;
+      else if (i0 == k) a0 = V[GV_C + jp];
+      if (i1 < k) a1 = gram_G(T, ld, P[i1], jp), r1 = T + i1 + 1, st1 = ld;
+      else if (i1 == k) a1 = V[GV_C + jp];
+      if (lane == 0) a0 += mu2;
+      const double *rp = T + p + 1;
+      if (k - p >= 32) {  // warp-uniform: more than 32 rows (with the right-hand side) are left
+        _Pragma("unroll 2") for (int q = 0; q < p; q++) {
+          const double lp = rp[q * ld];
+          a0 = fma(-r0[q * st0], lp, a0), a1 = fma(-r1[q * st1], lp, a1);
+        }
+      } else {
+        _Pragma("unroll 2") for (int q = 0; q < p; q++) a0 = fma(-r0[q * st0], rp[q * ld], a0);
+      }
+      const double d = __shfl_sync(DECAES_FULL_MASK, a0, 0);
+      if (!(d > 0.0)) return -1;
+      const double dinv = rsqrt(d);
+      // column p (and y_p) is written now; nobody reads it before the barrier below
+      if (lane == 0) GM_(p, p) = dinv;
+      else if (i0 < k) GM_(i0, p) = a0 * dinv;
+      else if (i0 == k) V[GV_Y + p] = a0 * dinv;
+      if (i1 < k) GM_(i1, p) = a1 * dinv;
+      else if (i1 == k) V[GV_Y + p] = a1 * dinv;
+      __syncwarp();
+    }
+    // back substitution s = L^-T y, y in registers (lane <-> positions lane, lane + 32)
+    double y0 = lane < k ? V[GV_Y + lane] : 0.0, y1 = lane + 32 < k ? V[GV_Y + lane + 32] : 0.0;
+    _Pragma("unroll 1") for (int p = k - 1; p >= 0; p--) {
+      const double yp = __shfl_sync(DECAES_FULL_MASK, p < 32 ? y0 : y1, p & 31);
+      const double sp = yp * GM_(p, p);
+      if (lane == (p & 31)) {
+        if (p < 32) s0 = sp;
+        else s1 = sp;
+      }
+      if (lane < p) y0 = fma(-GM_(p, lane), sp, y0);
+      if (lane + 32 < p) y1 = fma(-GM_(p, lane + 32), sp, y1);
+    }
+    const unsigned b0 = __ballot_sync(DECAES_FULL_MASK, lane < k && !(s0 > 0.0));
+    const unsigned b1 = __ballot_sync(DECAES_FULL_MASK, lane + 32 < k && !(s1 > 0.0));
+    const unsigned long long bad = ((unsigned long long)b1 << 32) | b0;
+    if (bad == 0ull) break;
+    unsigned long long drop = 0ull;
+    if (lane < k && !(s0 > 0.0)) drop |= 1ull << P[lane];
+    if (lane + 32 < k && !(s1 > 0.0)) drop |= 1ull << P[lane + 32];
+    mask &= ~warp_or64(drop);
+    p0 = __ffsll((long long)bad) - 1;
+    k = __popcll(mask);
+    __syncwarp();
+  }
+  // duals of the excluded columns: w_j = c_j - sum_t G(P[t], j) s_t must not be positive
+  const int pj0 = lane < k ? P[lane] : 0, pj1 = lane + 32 < k ? P[lane + 32] : 0;
+  _Pragma("unroll 1") for (unsigned long long ex = full & ~mask; ex; ex &= ex - 1ull) {
+    const int j = __ffsll((long long)ex) - 1;
+    double a = 0.0;
+    if (lane < k) a = gram_G(T, ld, pj0, j) * s0;
+    if (lane + 32 < k) a = fma(gram_G(T, ld, pj1, j), s1, a);
+    if (V[GV_C + j] - warp_sum(a) > 0.0) return -1;
+  }
+  if (lane < n) V[GV_X + lane] = 0.0;
+  if (lane + 32 < n) V[GV_X + lane + 32] = 0.0;
+  __syncwarp();
+  if (lane < k) V[GV_S + lane] = s0, V[GV_X + pj0] = s0;
+  if (lane + 32 < k) V[GV_S + lane + 32] = s1, V[GV_X + pj1] = s1;
+  double q2 = 0.0;
+  if (lane < k) q2 = s0 * s0;
+  if (lane + 32 < k) q2 = fma(s1, s1, q2);
+  xnorm_sq = warp_sum(q2);
+  __syncwarp();
   return k;
 }
 

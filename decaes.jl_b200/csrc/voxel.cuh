@@ -47,9 +47,13 @@ struct PipeParams {
   int sync_groups;          // 1: CTA-wide phase barriers; g > 1: one barrier per group of warps (warp id mod g)
   int sync_mask;            // which intra-round CTA barriers are active (bit 0: after flip angle, bit 1: after basis)
   int epg_smem;             // EPG at the fitted angle keeps its states in shared memory (lane <-> component)
+  int gcv_smem;             // Reg = gcv: the singular values are computed in shared memory during the basis phase (gcv_svdvals_smem)
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
-  int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too (default: only on the solves whose x is an output)
+  int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too: 1 = all probes, 2 = all but the seed probes
+  double kkt_tau;           // screening threshold of the polish: duals above -kkt_tau * max|c| are recomputed explicitly
   int fa_refine;            // iterative-refinement step on the flip-angle probes
+  int step_sync;            // CTA-wide votes inside the phases (cta_or): bit 0 = before every flip-angle probe, bit 1 = at every step of the
+                            // L-curve search, bit 2 = at its four initial points too, bit 3 = at every other regularised solve (Brent searches)
   int lc_hints;             // L-curve start hints: bit 0 = full column set at mu = e^2, bit 1 = flip-angle fit's set at mu = e^-8
   double angles[DECAES_MAX_ANGLES];                            // flip-angle grid (degrees)
   double logT2[DECAES_MAX_NT2], E2[DECAES_MAX_NT2];            // log(T2_j), exp(-(TE/2)/T2_j)
@@ -154,6 +158,29 @@ enum { PF_RHS = 0, PF_NNLS_UNREG, PF_RESID, PF_REFINE, PF_GRAD, PF_STAGE, PF_SUG
 __constant__ PipeParams cP;
 #define GL(p) __builtin_assume(__isGlobal(p))
 
+// CTA-wide OR on a barrier of its own (id 8): keeps the warps of a CTA in step INSIDE a phase.  The kernel is bound by
+// instruction fetch (ncu: the GPC-level instruction cache serves requests at 93-95 % of its peak rate when the twelve
+// warps of an SM wander through ~40 KB of hot code independently; the SM's own instruction cache hits 67-70 %).  Warps
+// that start every NNLS solve at the same time execute the same lines at about the same time and share them: +20 %
+// throughput for a vote per solve.  Protocol: a warp that has work votes true at each of its sync points; a warp that
+// is done with the phase (or has no voxel) keeps voting false until a vote comes back false (cta_drain).
+// Measured and rejected (profiles/r02_s2_ab_votes.txt): votes within groups of 6 or 4 warps (-6 % / -27 %: two or three
+// instruction streams per SM again), a vote every second or third L-curve step (-3 % / -4 %), votes at every
+// active-set iteration (-47 %), at the four initial L-curve points (-1 %), at every solve of the Brent searches (-6 %).
+__device__ __forceinline__ bool cta_or(bool pred) {
+  int r;
+  asm volatile(
+      "{\n.reg .pred p, q;\nsetp.ne.b32 p, %2, 0;\nbarrier.red.or.pred q, 8, %1, p;\nselp.b32 %0, 1, 0, q;\n}\n"
+      : "=r"(r)
+      : "r"((int)blockDim.x), "r"((int)pred)
+      : "memory");
+  return r != 0;
+}
+__device__ __noinline__ void cta_drain() {
+  while (cta_or(false)) {
+  }
+}
+
 // Member functions copy the pointers they use into locals and tell the compiler that they point to
 // shared memory: otherwise every access is a generic LD/ST, and every store forces a reload of the
 // members of *this (which lives in local memory) because it might alias them.
@@ -178,6 +205,7 @@ struct Warp {
   double *lc_pts_p, *lc_states_p, *slots_x_p, *fa_u_p, *fa_du_p;
   unsigned long long *fa_mask_p;
   double *bd, *sig, *fit, *slot_mu, *slot_lmu, *slot_r2, *slot_x2;
+  int solve_vote = 0;               // step_sync bit that makes the regularised solves vote right now (0: they do not)
   unsigned long long fa_mask_best;  // active set of the probed grid angle nearest to the fitted one (0 = none)
   uint64_t *bar;
   unsigned phase;
@@ -407,6 +435,7 @@ struct Warp {
       else if (cP.nTE <= 63) epg_basis_shfl<false>(alpha, v);
       else epg_basis_shfl<true>(alpha, v);
       PROF_END(7);
+      if (cP.reg == 2 && cP.gcv_smem) gcv_svdvals_smem(g + sl.pristine, V);
       PROF_BEGIN(8);
       gram_build(g + sl.pristine);
       PROF_END(8);
@@ -418,6 +447,7 @@ struct Warp {
 
   __device__ void fa_probe(int I, unsigned long long &seen, int &numeval) {
     double u, du;
+    if (cP.step_sync & 1) cta_or(true);
     if constexpr (GRAM) fa_eval_gram(I, u, du, seen);
     else fa_eval(I, u, du);
     if (lane == 0) fa_u_p[I] = u, fa_du_p[I] = du;
@@ -860,14 +890,17 @@ struct Warp {
     sx[2] = sx[0] + (sx[3] - sx[1]);
     // first point (mu = e^-8: practically the unregularised problem) starts from the flip-angle fit's active set,
     // the last one (mu = e^2) from the full column set
+    solve_vote = 4;
     for (int q = 0; q < 4; q++) si[q] = lc_eval(sx[q], npts, Asrc, q == 0 ? (cP.lc_hints & 2) : (q == 3 ? (cP.lc_hints & 1) : 0));
     const double tlx = pts[4 * si[0] + 1], tly = pts[4 * si[0] + 2], brx = pts[4 * si[3] + 1], bry = pts[4 * si[3] + 2];
     lc_update_curvature(sx, si, npts, tlx, tly, brx, bry, Ctol);
     int iter = 0;
+    solve_vote = 0;  // the steps below vote at the top of the loop (one vote per step, cache hit or not)
     while (true) {
       double p1x = pts[4 * si[0] + 1], p1y = pts[4 * si[0] + 2], p4x = pts[4 * si[3] + 1], p4y = pts[4 * si[3] + 2];
       if (fabs(sx[3] - sx[0]) < xtol || norm2(p1x, p1y, p4x, p4y) < Ptol) break;
       iter++;
+      if (cP.step_sync & 2) cta_or(true);
       {  // backtracking  :892-900
         double xb = pts[4 * lc_argmax(npts)];
         int kb = lc_backtrack(xb, fabs(sx[3] - sx[0]), nst);
@@ -1075,6 +1108,69 @@ struct Warp {
     }
     __syncwarp();
   }
+  // Singular values of the voxel's basis for Reg = gcv, in SHARED memory and with the column pairs of a one-sided
+  // Jacobi sweep handled in PARALLEL: lane <-> pair of a round-robin round (c / 2 disjoint pairs, c - 1 rounds per
+  // sweep), every lane runs its own dot products and its own rotation - no warp reductions, no barriers inside a
+  // round.  (The first version kept the matrix in global scratch and swept the pairs one after the other with
+  // lane <-> row: 56 M warp-cycles per voxel.)  Runs in the basis phase, when everything in front of the voxel's
+  // signal is free: the r x c matrix (r = max(nTE, nT2) >= c) sits at the start of the warp's shared memory, row-major.
+  __device__ __noinline__ void gcv_svdvals_smem(const double *Asrc, double *B) {
+    SH(B);
+    GL(Asrc);
+    const int lane = this->lane;
+    const int m = cP.nTE, n = cP.nT2, ld = cP.ld;
+    const int r = m >= n ? m : n, c = m >= n ? n : m;
+    _Pragma("unroll 1") for (int k = lane; k < m * n; k += 32) {
+      const int i = k / n, j = k - i * n;  // coalesced over the row-major source
+      const double v = Asrc[i * ld + j];
+      if (m >= n) B[i * c + j] = v;
+      else B[j * c + i] = v;
+    }
+    __syncwarp();
+    const int ce = (c + 1) & ~1, npair = ce >> 1;  // odd c: one dummy column (index c), its pair sits the round out
+    _Pragma("unroll 1") for (int sweep = 0; sweep < 60; sweep++) {
+      bool rotated = false;
+      _Pragma("unroll 1") for (int rd = 0; rd < ce - 1; rd++) {
+        // round-robin tournament: column ce - 1 stays, the others rotate
+        int p = ce - 1, q = rd;
+        if (lane > 0) p = (rd + lane) % (ce - 1), q = (rd + (ce - 1) - lane) % (ce - 1);
+        if (lane < npair && p < c && q < c) {
+          if (p > q) {
+            const int t = p;
+            p = q, q = t;
+          }
+          double al = 0.0, be = 0.0, ga = 0.0;
+          _Pragma("unroll 4") for (int i = 0; i < r; i++) {
+            const double up = B[i * c + p], uq = B[i * c + q];
+            al = fma(up, up, al), be = fma(uq, uq, be), ga = fma(up, uq, ga);
+          }
+          if (!(ga == 0.0 || fabs(ga) <= DBL_EPSILON * sqrt(al * be))) {
+            rotated = true;
+            const double zeta = (be - al) / (2 * ga);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+            const double cs = 1 / sqrt(1 + t * t), sn = cs * t;
+            _Pragma("unroll 4") for (int i = 0; i < r; i++) {
+              const double up = B[i * c + p], uq = B[i * c + q];
+              B[i * c + p] = cs * up - sn * uq;
+              B[i * c + q] = sn * up + cs * uq;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (!__any_sync(DECAES_FULL_MASK, rotated)) break;
+    }
+    double *gam = g + sl.gcv_gamma;
+    GL(gam);
+    _Pragma("unroll 1") for (int j = lane; j < c; j += 32) {
+      double s2 = 0.0;
+      _Pragma("unroll 4") for (int i = 0; i < r; i++) s2 = fma(B[i * c + j], B[i * c + j], s2);
+      gam[j] = sqrt(s2);
+    }
+    __threadfence_block();
+    __syncwarp();
+  }
+
   __device__ __noinline__ double gcv_fun(double logmu, const double *Asrc) {  // log(max(gcv, eps^2/m))  :1150-1154, 1213-1229
     const int m = cP.nTE, n = cP.nT2;
     double mu = exp(logmu);
@@ -1242,8 +1338,8 @@ struct Warp {
 
   // Explicit duals of the columns whose normal-equation dual (left in gws.w by gram_nnls) is not clearly negative:
   // w_j = A_j' r with r = b - A_P s in `fit`.  Returns the column with the largest positive explicit dual (first on
-  // ties, like largest_positive_dual, src/NNLS.jl:541-554) or -1.  "Clearly negative" = below -1e-6 max|c| (the
-  // maximum is taken on the upper halves of the doubles, one REDUX: the threshold is a screening heuristic, four
+  // ties, like largest_positive_dual, src/NNLS.jl:541-554) or -1.  "Clearly negative" = below -kkt_tau max|c| (kkt_tau = 1e-8; the
+  // maximum is taken on the upper halves of the doubles, one REDUX: the threshold is a screening heuristic, two
   // orders of magnitude above the noise the normal-equation dual was seen to carry).  lane <-> echo; two candidate
   // columns per L2 round trip.  Written for size: almost every call finds zero to two candidates.
   __device__ __noinline__ int kkt_pick(const double *Acm, unsigned long long excl) {
@@ -1256,7 +1352,7 @@ struct Warp {
     const int j0 = lane < n ? lane : 0, j1 = lane + 32 < n ? lane + 32 : 0;
     const double cm = fmax(lane < n ? fabs(cvec[j0]) : 0.0, lane + 32 < n ? fabs(cvec[j1]) : 0.0);
     const unsigned hi = __reduce_max_sync(DECAES_FULL_MASK, (unsigned)__double2hiint(cm));
-    const double tau = -1e-6 * __hiloint2double((int)hi, 0);
+    const double tau = -cP.kkt_tau * __hiloint2double((int)hi, 0);
     const unsigned c0 = __ballot_sync(DECAES_FULL_MASK, lane < n && !((excl >> j0) & 1ull) && gws.w[j0] > tau);
     const unsigned c1 = __ballot_sync(DECAES_FULL_MASK, lane + 32 < n && !((excl >> j1) & 1ull) && gws.w[j1] > tau);
     unsigned long long cand = ((unsigned long long)c1 << 32) | c0;
@@ -1383,9 +1479,9 @@ struct Warp {
       if (abs(kang - jn) <= cP.fa_warm) warm = fa_mask_p[jn];
     }
     GramOut o;
-    // The probes only feed the loss and its slope to the surrogate: a column with a dual of +1e-10 left out of the
-    // active set moves neither beyond 1e-10, so the KKT polish is reserved for the solves whose x is an output.
-    u = gram_solve_unreg(src, o, warm, cP.fa_refine != 0, cP.fa_polish != 0);
+    // fa_polish = 0 leaves the KKT polish to the solves whose x is an output (+1.2 % throughput; one voxel in 2,048 of the
+    // three-pool stress family then misses the flip-angle tolerance: 1.4e-6 instead of 3.4e-7)
+    u = gram_solve_unreg(src, o, warm, cP.fa_refine != 0, cP.fa_polish == 1 || (cP.fa_polish == 2 && __popcll(seen) >= cP.nseed));
     if (lane == 0) fa_mask_p[kang] = o.mask;
     const double *dAk = cP.dbasis_cm + (size_t)kang * nTE * n;
     GL(dAk);
@@ -1549,6 +1645,7 @@ struct Warp {
     }
     const unsigned nanm = __ballot_sync(DECAES_FULL_MASK, isl && isnan(mui));
     cur_slot = nanm ? __ffs(nanm) - 1 : (cur_slot + 1) % DECAES_NCACHE;
+    if (cP.step_sync & solve_vote) cta_or(true);
     const double mu2 = __dmul_rn(mu, mu);
     if (isnan(lmu)) lmu = dlog(mu);
     unsigned long long wmask = 0ull;
@@ -1575,7 +1672,21 @@ struct Warp {
     }
     GramOut o;
     PROF_BEGIN(9);
-    o = gram_nnls<VS>(V, n, cP.ldg, mu2, n, wmask != 0ull, wmask);
+    bool solved = false;
+    if (hint == 1 && (cP.lc_hints & 4)) {
+      unsigned long long m = wmask;
+      double xn;
+      const int kd = gram_dense_solve<VS>(V, n, cP.ldg, mu2, m, xn);
+      if (kd >= 0) {
+        o.k = kd, o.mask = m, o.xnorm_sq = xn, o.iters = 1, o.nappend = 0, o.capped = false;
+        solved = true;
+      } else {
+        if (m) wmask = m;
+        _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = ((wmask >> j) & 1ull) ? 1.0 : 0.0;
+        __syncwarp();
+      }
+    }
+    if (!solved) o = gram_nnls<VS>(V, n, cP.ldg, mu2, n, wmask != 0ull, wmask);
     n_itercap += o.capped;
 #ifdef DECAES_PROFILE
     if (lane == 0) {
@@ -1633,6 +1744,7 @@ struct Warp {
     if (cP.alpha_provided) alpha_cur = cP.alpha[v];
     else if (cP.fixed_alpha) alpha_cur = cP.SetFlipAngle;
     else alpha_cur = optimize_flip_angle();
+    if (cP.step_sync & 1) cta_drain();
   }
 
   // phase 2: EPG basis at the fitted angle (+ Gram matrix / right-hand side)
@@ -1640,6 +1752,7 @@ struct Warp {
     if (cP.fixed_alpha && !cP.alpha_provided) {
       if constexpr (GRAM) {
         cursrc.G = cP.gram_set, cursrc.ldg = cP.ldg, cursrc.Arm = cP.basis_rm, cursrc.Acm = cP.basis_cm;
+        if (cP.reg == 2 && cP.gcv_smem) gcv_svdvals_smem(cP.basis_rm, V);
         stage_bulk(Gs, cP.gram_set, (unsigned)(cP.a_elems * 8));
         gram_rhs(cursrc.Arm);
       }
@@ -1685,7 +1798,8 @@ struct Warp {
         }
       } break;
       case 2: {  // lsqnonneg_gcv!  src/lsqnonneg.jl:1136-1205
-        gcv_svdvals(Asrc);
+        solve_vote = 8;
+        if (!(GRAM && cP.gcv_smem)) gcv_svdvals(Asrc);
         cache_reset();
         double logmu = gcv_minimize(Asrc);
         mu = exp(logmu);
@@ -1699,6 +1813,7 @@ struct Warp {
       } break;
       case 3:    // lsqnonneg_chi2!  src/lsqnonneg.jl:504-593
       case 4: {  // lsqnonneg_mdp!   src/lsqnonneg.jl:700-747
+        solve_vote = 8;
         NnlsOut o = solve_unreg(Asrc);
         double res2_min = o.rnorm_sq;
         bool early = false;
@@ -1760,6 +1875,8 @@ struct Warp {
       } break;
     }
 
+    solve_vote = 0;
+    if (cP.step_sync & 14) cta_drain();  // the one drain of this phase (warps without a voxel: the kernel's main loop)
     // save_results!  src/T2mapSEcorr.jl:512-591
     double *xs = ws.w;  // dual no longer needed
     {
