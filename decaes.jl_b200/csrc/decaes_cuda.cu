@@ -784,6 +784,12 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if (const char *e = getenv("DECAES_EPG_SMEM")) P.epg_smem = P.epg_smem && atoi(e);
   P.gcv_smem = P.gram && o->reg == DECAES_REG_GCV && nTE * nT2 <= L.bd && std::min(nTE, nT2) <= 64;
   if (const char *e = getenv("DECAES_GCV_SMEM")) P.gcv_smem = P.gcv_smem && atoi(e);
+  // one copy of the voxel's basis in the global scratch (column-major) unless someone needs the row-major one too: the QR
+  // port (TMA source), the shuffle EPG (no on-the-fly right-hand side), the global-memory SVD of Reg = gcv
+  P.need_rm = !P.gram || !P.epg_smem || (o->reg == DECAES_REG_GCV && !P.gcv_smem);
+  if (const char *e = getenv("DECAES_NEED_RM")) P.need_rm = P.need_rm || atoi(e);
+  P.epg_fuse = 1;
+  if (const char *e = getenv("DECAES_EPG_FUSE")) P.epg_fuse = atoi(e) != 0;
   P.refcon = o->RefConAngle;
   if (P.refcon != 180.0 && !fixed && !(P.gram && 3 * P.epg_kmax * P.epg_lanes <= L.bd))
     return fail(DECAES_EUNSUPPORTED, "RefConAngle != 180 needs the Gram solver and %d bytes of shared EPG scratch per warp", 3 * P.epg_kmax * P.epg_lanes * 8);
@@ -822,7 +828,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   CUDA_TRY(cudaFuncSetAttribute(pipeline_kernel_for(P), cudaFuncAttributeMaxDynamicSharedMemorySize, plan->cta_smem));
   plan->grid = prop.multiProcessorCount;
 
-  ScratchLayout sl(nTE, nT2, P.copy_elems, o->reg == DECAES_REG_GCV);
+  ScratchLayout sl(nTE, nT2, P.copy_elems, o->reg == DECAES_REG_GCV, P.need_rm != 0);
   P.scratch_per_warp = sl.total;
 
   std::lock_guard<std::mutex> lk(g_ws_mutex);
@@ -896,7 +902,7 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
   int64_t ngroups = (nvox + DECAES_GROUP - 1) / DECAES_GROUP;
   int grid = (int)std::min<int64_t>(plan.grid, std::max<int64_t>((ngroups + plan.warps_per_cta - 1) / plan.warps_per_cta, 1));
   CUDA_TRY(cudaMemcpyToSymbolAsync(cP, &P, sizeof(PipeParams), 0, cudaMemcpyHostToDevice, stream));
-  // Keep the per-warp scratch (the voxel's basis in both layouts, ~46 KB per warp, rewritten for every voxel)
+  // Keep the per-warp scratch (the voxel's basis, 27 KB per warp - 46 KB with the row-major copy - rewritten for every voxel)
   // resident in L2: without the window the streaming image / output traffic evicts it and every basis is
   // written back to and re-read from HBM (ncu: 19 KB of DRAM writes per voxel).
   const size_t scratch_bytes = (size_t)plan.grid * plan.warps_per_cta * P.scratch_per_warp * sizeof(double);
@@ -908,9 +914,14 @@ static int launch_pipeline(Plan &plan, int dev, const double *d_image, int64_t n
     attr.accessPolicyWindow.num_bytes = std::min(scratch_bytes, ws.l2_window_max);
     attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ws.l2_persist_max / (double)attr.accessPolicyWindow.num_bytes);
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    attr.accessPolicyWindow.missProp = getenv("DECAES_L2_MISS_NORMAL") ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
+    if (const char *e = getenv("DECAES_L2_HIT_RATIO")) attr.accessPolicyWindow.hitRatio = (float)atof(e);
     window = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
     if (!window) cudaGetLastError();
+    if (getenv("DECAES_PHASE_CYCLES"))
+      fprintf(stderr, "[decaes] L2 window: scratch %.1f MB, persisting carve-out %.1f MB, largest window %.1f MB, hit ratio %.3f, set: %d\n",
+              scratch_bytes / 1048576.0, ws.l2_persist_max / 1048576.0, ws.l2_window_max / 1048576.0,
+              (double)attr.accessPolicyWindow.hitRatio, (int)window);
   }
   pipeline_kernel_for(P)<<<grid, 32 * plan.warps_per_cta, plan.cta_smem, stream>>>(P);
   CUDA_TRY(cudaGetLastError());

@@ -47,6 +47,8 @@ struct PipeParams {
   int sync_groups;          // 1: CTA-wide phase barriers; g > 1: one barrier per group of warps (warp id mod g)
   int sync_mask;            // which intra-round CTA barriers are active (bit 0: after flip angle, bit 1: after basis)
   int epg_smem;             // EPG at the fitted angle keeps its states in shared memory (lane <-> component)
+  int epg_fuse;             // shared-memory EPG: two echoes per sweep over the states
+  int need_rm;              // the voxel's basis is also kept row-major in the global scratch (0: column-major only, c = A'b comes out of the EPG)
   int gcv_smem;             // Reg = gcv: the singular values are computed in shared memory during the basis phase (gcv_svdvals_smem)
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
   int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too: 1 = all probes, 2 = all but the seed probes
@@ -67,9 +69,10 @@ struct PipeParams {
 // layout of the per-warp global scratch (in doubles)
 struct ScratchLayout {
   int pristine, pristine_cm, slots_x, lc_pts, lc_states, fa_u, fa_du, fa_mask, gcv_gamma, gcv_mat, total;
-  __host__ __device__ ScratchLayout(int nTE, int nT2, int copy_elems, bool gcv) {
+  // rm: keep a row-major copy of the voxel's basis next to the column-major one (QR port, shuffle EPG, global-memory SVD)
+  __host__ __device__ ScratchLayout(int nTE, int nT2, int copy_elems, bool gcv, bool rm = true) {
     int o = 0;
-    pristine = o, o += copy_elems;
+    pristine = o, o += rm ? copy_elems : 0;
     pristine_cm = o, o += nTE * nT2 + (nTE * nT2 & 1);
     slots_x = o, o += DECAES_NCACHE * nT2;
     lc_pts = o, o += DECAES_LC_MAX * 4;
@@ -205,6 +208,7 @@ struct Warp {
   double *lc_pts_p, *lc_states_p, *slots_x_p, *fa_u_p, *fa_du_p;
   unsigned long long *fa_mask_p;
   double *bd, *sig, *fit, *slot_mu, *slot_lmu, *slot_r2, *slot_x2;
+  double c_epg[2];                  // c = A'b of the fitted-angle basis, accumulated by the shared-memory EPG (one entry per pass)
   int solve_vote = 0;               // step_sync bit that makes the regularised solves vote right now (0: they do not)
   unsigned long long fa_mask_best;  // active set of the probed grid angle nearest to the fitted one (0 = none)
   uint64_t *bar;
@@ -218,7 +222,7 @@ struct Warp {
   int nsolve_voxel = 0, nunreg_voxel = 0;  // Tikhonov / unregularised solves of the current voxel (DECAES_PROFILE)
 
   __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
-      : sl(p.nTE, p.nT2, p.copy_elems, p.reg == 2) {
+      : sl(p.nTE, p.nT2, p.copy_elems, p.reg == 2, p.need_rm != 0) {
     SmemLayout L(p.nTE, p.nT2, p.rows_alloc, p.a_elems, p.gram, p.spill, p.gv_stride);
     ws.A = smem + L.A, ws.b = smem + L.b, ws.u = smem + L.u, ws.x = smem + L.x, ws.w = smem + L.w;
     ws.idx = (int *)(smem + L.idx);
@@ -435,9 +439,19 @@ struct Warp {
       else if (cP.nTE <= 63) epg_basis_shfl<false>(alpha, v);
       else epg_basis_shfl<true>(alpha, v);
       PROF_END(7);
-      if (cP.reg == 2 && cP.gcv_smem) gcv_svdvals_smem(g + sl.pristine, V);
+      // the basis lives column-major in the scratch; a row-major copy (element (i, j) at i * ld + j) only when need_rm
+      const bool rm = cP.need_rm != 0;
+      const double *Ab = rm ? g + sl.pristine : g + sl.pristine_cm;
+      const int rs = rm ? cP.ld : 1, cs = rm ? 1 : cP.nTE;
+      if (cP.reg == 2 && cP.gcv_smem) gcv_svdvals_smem(Ab, rs, cs, V);
+      if (!rm && cP.epg_smem) {  // right-hand side c = A'b straight from the EPG's registers
+        const int LW = cP.epg_lanes;
+        if (lane < LW && lane < cP.nT2) cvec[lane] = c_epg[0];
+        if (lane < LW && LW + lane < cP.nT2) cvec[LW + lane] = c_epg[1];
+        __syncwarp();
+      }
       PROF_BEGIN(8);
-      gram_build(g + sl.pristine);
+      gram_build(Ab, rs, cs, rm || !cP.epg_smem);
       PROF_END(8);
       cursrc.G = Gs, cursrc.ldg = cP.ldg, cursrc.Arm = g + sl.pristine, cursrc.Acm = g + sl.pristine_cm;
     } else {
@@ -520,6 +534,8 @@ struct Warp {
     double *pc = GRAM ? g + sl.pristine_cm : pr;
     GL(pr);
     GL(pc);
+    VIEW(double, bd);
+    const bool rm = !GRAM || cP.need_rm != 0;  // row-major copy wanted (otherwise column-major only, and c = A'b on the fly)
     double sina, cosa;
     sincos(alpha_deg * 0.017453292519943295, &sina, &cosa);
     const double m0 = sind_0_180(alpha_deg / 2);
@@ -547,22 +563,59 @@ struct Warp {
   vF = fma(c, Z, __dadd_rn(Cp, Sp));            \
   vZ = fma(cp, Sd, __dmul_rn(d, Z))
         double dc = __dsub_rn(a, b);
+        double cacc;  // c_j = sum_i A(i, j) b_i in gram_atv's order (i ascending, fma)
         {
           const double val = fabs(__dmul_rn(m0, dc));
-          pr[0 * ld + j] = val;
+          if (rm) pr[0 * ld + j] = val;
           if (GRAM) pc[j * ETL] = val;
+          cacc = fma(val, bd[0], 0.0);
         }
         ST(0, 1) = __dsub_rn(a, b), ST(1, 1) = 0.0, ST(2, 1) = cp;
         ST(0, 2) = __dadd_rn(a, b), ST(1, 2) = 0.0, ST(2, 2) = 0.0;
-        for (int i = 2; i <= ETL - 1; i++) {
+        // Two echoes per sweep over the states when both lie in the same half of the train (the state count grows by
+        // one per echo in the first half and shrinks by one in the second): echo i at state k + 1 feeds echo i + 1 at
+        // state k (new F_k = F'_{k-1}, new Fbar_k = Fbar'_{k+1}, new Z_k = Z'_k), so one pass of 3 loads + 3 stores per
+        // state carries two updates - the phase is bound by the shared-memory pipe.  Same operations on the same
+        // values as one echo at a time (bit-identical basis; DECAES_EPG_FUSE=0 for the A/B).
+        int i = 2;
+        while (i <= ETL - 1) {
           const bool first_half = (i <= ETL / 2);
           const int kmax = first_half ? i : ETL - i + 1;
           F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
           UPD();
           {
             const double val = fabs(__dmul_rn(m0, vFb));
-            pr[(i - 1) * ld + j] = val;
+            if (rm) pr[(i - 1) * ld + j] = val;
             if (GRAM) pc[j * ETL + i - 1] = val;
+            cacc = fma(val, bd[i - 1], cacc);
+          }
+          if (cP.epg_fuse && i + 1 <= ETL - 1 && ((i + 1 <= ETL / 2) == first_half)) {
+            const int ka = kmax, kb = first_half ? ka + 1 : ka - 1;
+            double f2 = vFb, f1 = vF, z1 = vZ;  // new F_1 (= Fbar'_1), F'_1 (-> new F_2), new Z_1
+            DECAES_PRAGMA(unroll DECAES_EPG_UNROLL) for (int k = 1; k <= kb; k++) {
+              double nFb = 0.0, nf1 = 0.0, nz1 = 0.0;  // first half: the states beyond ka are zero after echo i
+              if (k + 1 <= ka) {
+                F = ST(0, k + 1), Fb = ST(1, k + 1), Z = ST(2, k + 1);  // echo i at state k + 1
+                UPD();
+                nFb = vFb, nf1 = vF, nz1 = vZ;
+              }
+              F = f2, Fb = nFb, Z = z1;  // echo i + 1 at state k
+              UPD();
+              if (k == 1) {
+                const double val = fabs(__dmul_rn(m0, vFb));
+                if (rm) pr[i * ld + j] = val;
+                if (GRAM) pc[j * ETL + i] = val;
+                cacc = fma(val, bd[i], cacc);
+                ST(0, 1) = vFb;
+              } else {
+                ST(1, k - 1) = vFb;
+              }
+              ST(0, k + 1) = vF, ST(2, k) = vZ;
+              f2 = f1, f1 = nf1, z1 = nz1;
+            }
+            if (first_half) ST(1, i + 1) = 0.0, ST(1, i + 2) = 0.0, ST(2, i + 2) = 0.0;
+            i += 2;
+            continue;
           }
           ST(0, 1) = vFb, ST(2, 1) = vZ;
           double pend = vF;
@@ -576,15 +629,18 @@ struct Warp {
           }
           ST(0, kmax + 1) = pend;
           if (first_half) ST(1, i) = 0.0, ST(1, i + 1) = 0.0, ST(2, i + 1) = 0.0;
+          i += 1;
         }
         F = ST(0, 1), Fb = ST(1, 1), Z = ST(2, 1);
         C = __dadd_rn(F, Fb), Sd = __dsub_rn(F, Fb);
         dc = fma(-c, Z, fma(a, C, __dmul_rn(-b, Sd)));
         {
           const double val = fabs(__dmul_rn(m0, dc));
-          pr[(ETL - 1) * ld + j] = val;
+          if (rm) pr[(ETL - 1) * ld + j] = val;
           if (GRAM) pc[j * ETL + ETL - 1] = val;
+          cacc = fma(val, bd[ETL - 1], cacc);
         }
+        c_epg[j0 != 0] = cacc;  // at most two passes (LW >= nT2 / ceil(nT2 / 32))
       }
       __syncwarp();
     }
@@ -595,7 +651,7 @@ struct Warp {
       __syncwarp();
       for (int k = lane; k < ETL * n; k += 32) {
         int i = k % ETL, jj = k / ETL;
-        cP.decaybasis[v + (long long)k * cP.stride] = pr[i * ld + jj];
+        cP.decaybasis[v + (long long)k * cP.stride] = GRAM ? pc[k] : pr[i * ld + jj];
       }
     }
     __threadfence_block();
@@ -614,6 +670,8 @@ struct Warp {
     double *pr = g + sl.pristine, *pc = g + sl.pristine_cm;
     GL(pr);
     GL(pc);
+    VIEW(double, bd);
+    const bool rm = cP.need_rm != 0;
     const double kk = 0.017453292519943295;
     const double A = alpha_deg / 180;
     double sh, ch, sini, cosi;
@@ -633,12 +691,14 @@ struct Warp {
         const double a1 = __dmul_rn(E2sq, c2h), b1 = __dmul_rn(E2sq, s2h), c1 = __dmul_rn(E1E2, sin1);
         const double ai = __dmul_rn(E2sq, c2hi), bi = __dmul_rn(E2sq, s2hi), ci = __dmul_rn(E1E2, sini);
         const double di = __dmul_rn(__dmul_rn(E1, E1), cosi), hci = ci / 2;
-        double mF, mFb, mZ, FM, FbM, ZM;
+        double mF, mFb, mZ, FM, FbM, ZM, cacc;
         ST(0, 1) = __dmul_rn(b1, m0), ST(1, 1) = 0.0, ST(2, 1) = __dmul_rn(-c1, m0) / 2;
         ST(0, 2) = __dmul_rn(a1, m0), ST(1, 2) = 0.0, ST(2, 2) = 0.0;
         {
           const double val = fabs(__dmul_rn(b1, m0));
-          pr[j] = val, pc[j * ETL] = val;
+          if (rm) pr[j] = val;
+          pc[j * ETL] = val;
+          cacc = fma(val, bd[0], 0.0);
         }
         _Pragma("unroll 1") for (int i = 2; i <= ETL - 1; i++) {
           const bool first_half = (i <= ETL / 2);
@@ -647,7 +707,9 @@ struct Warp {
           FM = DOT3(ai, bi, ci), FbM = DOT3(bi, ai, -ci), ZM = DOT3(-hci, hci, di);
           {
             const double val = fabs(FbM);
-            pr[(i - 1) * ld + j] = val, pc[j * ETL + i - 1] = val;
+            if (rm) pr[(i - 1) * ld + j] = val;
+            pc[j * ETL + i - 1] = val;
+            cacc = fma(val, bd[i - 1], cacc);
           }
           ST(0, 1) = FbM, ST(2, 1) = ZM;
           double pend = FM;
@@ -664,8 +726,11 @@ struct Warp {
         mF = ST(0, 1), mFb = ST(1, 1), mZ = ST(2, 1);
         {
           const double val = fabs(DOT3(bi, ai, -ci));
-          pr[(ETL - 1) * ld + j] = val, pc[j * ETL + ETL - 1] = val;
+          if (rm) pr[(ETL - 1) * ld + j] = val;
+          pc[j * ETL + ETL - 1] = val;
+          cacc = fma(val, bd[ETL - 1], cacc);
         }
+        c_epg[j0 != 0] = cacc;
       }
       __syncwarp();
     }
@@ -1114,15 +1179,15 @@ struct Warp {
   // round.  (The first version kept the matrix in global scratch and swept the pairs one after the other with
   // lane <-> row: 56 M warp-cycles per voxel.)  Runs in the basis phase, when everything in front of the voxel's
   // signal is free: the r x c matrix (r = max(nTE, nT2) >= c) sits at the start of the warp's shared memory, row-major.
-  __device__ __noinline__ void gcv_svdvals_smem(const double *Asrc, double *B) {
+  __device__ __noinline__ void gcv_svdvals_smem(const double *Asrc, int rs, int cs, double *B) {  // element (i, j) at i * rs + j * cs
     SH(B);
     GL(Asrc);
     const int lane = this->lane;
-    const int m = cP.nTE, n = cP.nT2, ld = cP.ld;
+    const int m = cP.nTE, n = cP.nT2;
     const int r = m >= n ? m : n, c = m >= n ? n : m;
     _Pragma("unroll 1") for (int k = lane; k < m * n; k += 32) {
-      const int i = k / n, j = k - i * n;  // coalesced over the row-major source
-      const double v = Asrc[i * ld + j];
+      const int i = k / n, j = k - i * n;
+      const double v = Asrc[i * rs + j * cs];
       if (m >= n) B[i * c + j] = v;
       else B[j * c + i] = v;
     }
@@ -1580,15 +1645,16 @@ struct Warp {
     }
   }
 
-  // G = A'A (lower triangle) and c = A'bd from the row-major basis in global scratch into shared memory.
+  // G = A'A (lower triangle) and, with `rhs`, c = A'bd from the basis in global scratch (element (i, j) at i * rs + j * cs:
+  // row-major rs = ld, cs = 1; column-major rs = 1, cs = nTE) into shared memory.
   // The Gram contraction runs on the FP64 tensor cores: mma.sync m8n8k4 with D(p, q) += sum over four
   // echoes of A(i, p) A(i, q); both operand fragments are the SAME load pattern (lane (g, t) holds
   // A[i0 + t][8 c + g]), one 8-column tile row of G at a time.
-  __device__ __noinline__ void gram_build(const double *Arm) {
+  __device__ __noinline__ void gram_build(const double *Arm, int rs, int cs, bool rhs) {
     GL(Arm);
     const int lane = this->lane;
     VIEW(double, Gs);
-    const int nTE = cP.nTE, n = cP.nT2, ld = cP.ld, ldg = cP.ldg;
+    const int nTE = cP.nTE, n = cP.nT2, ldg = cP.ldg;
     const int g = lane >> 2, t = lane & 3;
     const int NT = (n + 7) >> 3;
     _Pragma("unroll 1") for (int cp = 0; cp < NT; cp++) {
@@ -1598,12 +1664,13 @@ struct Warp {
       const bool pv = 8 * cp + g < n;
       _Pragma("unroll 1") for (int i0 = 0; i0 < nTE; i0 += 4) {
         const bool iv = i0 + t < nTE;
-        const double *row = Arm + (iv ? i0 + t : 0) * ld + g;
-        const double fa = (iv && pv) ? row[8 * cp] : 0.0;
+        const double *row = Arm + (iv ? i0 + t : 0) * rs + g * cs;
+        const int c8 = 8 * cs;
+        const double fa = (iv && pv) ? row[cp * c8] : 0.0;
         double f[8];
 #pragma unroll
         for (int cq = 0; cq < 8; cq++)
-          if (cq <= cp) f[cq] = (iv && 8 * cq + g < n) ? row[8 * cq] : 0.0;
+          if (cq <= cp) f[cq] = (iv && 8 * cq + g < n) ? row[cq * c8] : 0.0;
 #pragma unroll
         for (int cq = 0; cq < 8; cq++)
           if (cq <= cp)
@@ -1621,7 +1688,7 @@ struct Warp {
         }
     }
     __syncwarp();
-    gram_rhs(Arm);
+    if (rhs) gram_rhs(Arm);  // (row-major only; the shared-memory EPG accumulates c on the fly)
   }
 
   // solve!(cache, mu) for the Gram solver: exact-mu hit, else warm-start from the nearest cached mu (lane <-> slot)
@@ -1752,7 +1819,7 @@ struct Warp {
     if (cP.fixed_alpha && !cP.alpha_provided) {
       if constexpr (GRAM) {
         cursrc.G = cP.gram_set, cursrc.ldg = cP.ldg, cursrc.Arm = cP.basis_rm, cursrc.Acm = cP.basis_cm;
-        if (cP.reg == 2 && cP.gcv_smem) gcv_svdvals_smem(cP.basis_rm, V);
+        if (cP.reg == 2 && cP.gcv_smem) gcv_svdvals_smem(cP.basis_rm, cP.ld, 1, V);
         stage_bulk(Gs, cP.gram_set, (unsigned)(cP.a_elems * 8));
         gram_rhs(cursrc.Arm);
       }
