@@ -142,6 +142,9 @@ struct Src {               // where the current basis of the Gram solver lives
 
 #define DECAES_PRAGMA_(x) _Pragma(#x)
 #define DECAES_PRAGMA(x) DECAES_PRAGMA_(x)
+#ifndef DECAES_RESID_CHUNK
+#define DECAES_RESID_CHUNK 4  // columns per L2 round trip of the explicit residual (8: +0.5 % on cfg3, -3 % on the nT2 = 60 configs)
+#endif
 #ifndef DECAES_EPG_UNROLL
 #define DECAES_EPG_UNROLL 1  // state loop of the shared-memory EPG (independent iterations: unrolling buys ILP, costs code)
 #endif
@@ -1314,10 +1317,11 @@ struct Warp {
     SH(bd);
     SH(cvec);
     const int nTE = cP.nTE, ld = cP.ld, n = cP.nT2;
-    // lane <-> columns lane and lane + 32: both advance together, 16 loads in flight (the matrix lives in L2)
+    // lane <-> columns lane and lane + 32: both advance together, 16 loads in flight (the matrix lives in L2).  Deeper
+    // chunks (32 loads in flight) buy 0.3 % on cfg3 and cost 3 % on the nT2 = 60 configs (code size), so: unroll 8.
     const double *c0 = Arm + (lane < n ? lane : 0), *c1 = Arm + (lane + 32 < n ? lane + 32 : 0);
     double a0 = 0.0, a1 = 0.0;
-    _Pragma("unroll 4") for (int i = 0; i < nTE; i++) {
+    _Pragma("unroll 8") for (int i = 0; i < nTE; i++) {
       const double bi = bd[i];
       a0 = fma(c0[i * ld], bi, a0), a1 = fma(c1[i * ld], bi, a1);
     }
@@ -1338,10 +1342,23 @@ struct Warp {
     // trip serves up to 12 loads per lane (A lives in L2; the loop is latency bound)
     const int i0 = lane < nTE ? lane : 0, i1 = lane + 32 < nTE ? lane + 32 : i0, i2 = lane + 64 < nTE ? lane + 64 : i0;
     double r0 = bd[i0], r1 = bd[i1], r2 = bd[i2];
-    _Pragma("unroll 2") for (int t = 0; t < k; t++) {
-      const double *col = Acm + gws.P[t] * nTE;
-      const double st = gws.s[t];
-      r0 = fma(-col[i0], st, r0), r1 = fma(-col[i1], st, r1), r2 = fma(-col[i2], st, r2);
+    // columns in chunks of DECAES_RESID_CHUNK, every load of a chunk issued before its first fma (A lives in L2 and the loop
+    // is bound by its latency); slots beyond k repeat the chunk's first column with a zero coefficient: no branches, same sums
+    _Pragma("unroll 1") for (int tb = 0; tb < k; tb += DECAES_RESID_CHUNK) {
+      double v0[DECAES_RESID_CHUNK], v1[DECAES_RESID_CHUNK];
+#pragma unroll
+      for (int u = 0; u < DECAES_RESID_CHUNK; u++) {
+        const double *col = Acm + gws.P[tb + u < k ? tb + u : tb] * nTE;
+        v0[u] = col[i0], v1[u] = col[i1];
+      }
+#pragma unroll
+      for (int u = 0; u < DECAES_RESID_CHUNK; u++) {
+        const double st = tb + u < k ? gws.s[tb + u < k ? tb + u : tb] : 0.0;
+        r0 = fma(-v0[u], st, r0), r1 = fma(-v1[u], st, r1);
+      }
+    }
+    if (nTE > 64) {
+      _Pragma("unroll 2") for (int t = 0; t < k; t++) r2 = fma(-Acm[gws.P[t] * nTE + i2], gws.s[t], r2);
     }
     double acc = 0.0;
     if (lane < nTE) fit[i0] = r0, acc = __dmul_rn(r0, r0);

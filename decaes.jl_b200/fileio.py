@@ -149,9 +149,23 @@ def load_image(filename, ndims=4):
     return np.require(np.asfortranarray(data, dtype=np.float64), requirements=["F", "W", "O"])
 
 
+MAT5_MAX_BYTES = 2**31 - 2**20  # MAT v5 stores the byte count of a variable in 32 bits
+
+
 def save_mat(filename, variables):
-    """MAT.matwrite(savefile, dict): variable names and shapes as the reference writes them (MAT v5 container)."""
+    """MAT.matwrite(savefile, dict): variable names and shapes as the reference writes them (MAT v5 container).
+    A variable too large for MAT v5 (the reference writes v7.3 / HDF5, which this environment cannot) is written next
+    to the file as `<filename>.<name>.npy` instead of failing after the whole volume has been computed; the .mat file
+    then holds a string of that name pointing to it."""
     from scipy.io import savemat
     os.makedirs(os.path.dirname(os.path.abspath(filename)), exist_ok=True)
-    savemat(filename, {k: (np.asarray(v) if not np.isscalar(v) else v) for k, v in variables.items()}, do_compression=False,
-            oned_as="column")
+    out = {}
+    for k, v in variables.items():
+        a = v if np.isscalar(v) else np.asarray(v)
+        if not np.isscalar(a) and a.nbytes > MAT5_MAX_BYTES:
+            side = f"{filename}.{k}.npy"
+            np.save(side, a)
+            print(f"warning: {k} ({a.nbytes / 2**30:.1f} GiB) exceeds the MAT v5 limit; written to {side}")
+            a = f"see {os.path.basename(side)}"
+        out[k] = a
+    savemat(filename, out, do_compression=False, oned_as="column")

@@ -1,0 +1,21 @@
+#!/bin/bash
+# batch 14: A'b loop back to unroll 8; warm-start reach of the flip-angle probes
+mkdir -p gpurun_out
+run() { echo -n "[$1 $2] "; env $1 DECAES_PHASE_CYCLES=1 timeout 300 python bench.py --voxels ${VOX:-400000} --steps 2 --warmup 1 --no-e2e --no-cpu --parity-sample 0 $2 2>&1 | python -c "
+import sys,json
+t='';p=''
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('value', round(d['value']), 'kern_ms', round(d['kernel_ms_per_step'],1), 'chk', d['checksum_gdn'], t, p)
+    elif 'warp-cycles' in l: t=l.strip().split('voxel:')[-1]
+"; }
+{
+for r in 1 2; do
+run "X=0"
+run "DECAES_FA_WARM=8"
+run "DECAES_FA_WARM=16"
+run "DECAES_FA_WARM=2"
+done
+for wl in cfg1 cfg2 cfg4 cfg5; do run "X=0" "--workload $wl"; done
+run "X=0" "--mask 0.65"
+} 2>&1 | tee gpurun_out/r02s_ab.txt
