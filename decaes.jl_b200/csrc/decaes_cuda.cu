@@ -701,11 +701,15 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if (const char *e = getenv("DECAES_FA_WARM")) P.fa_warm = atoi(e);
   P.fa_polish = 1, P.fa_refine = 1;
   if (const char *e = getenv("DECAES_FA_POLISH")) P.fa_polish = atoi(e);
+  // seed probes without refinement / polish: +1 % (cfg3) to +4 % (cfg4, cfg5), but at SNR 15 the cruder loss slopes steer 3 of
+  // 2,048 voxels into another bracket of a flat loss (flip angle off by 0.07 degrees): off (profiles/r02_s2_ab_rough_seed_probes.txt)
+  P.fa_rough_seeds = 0;
+  if (const char *e = getenv("DECAES_FA_ROUGH_SEEDS")) P.fa_rough_seeds = atoi(e) != 0;
   P.kkt_tau = 1e-8;  // two orders of magnitude above the noise of the normal-equation duals (1e-6: three candidates per solve instead of one)
   if (const char *e = getenv("DECAES_KKT_TAU")) P.kkt_tau = atof(e);
   if (const char *e = getenv("DECAES_FA_REFINE")) P.fa_refine = atoi(e);
-  P.lc_hints = 7;  // bit 2: the full-set start is a direct Cholesky solve (gram_dense_solve)
-  if (const char *e = getenv("DECAES_LC_HINTS")) P.lc_hints = atoi(e) & 7;
+  P.lc_hints = 15;  // bit 2: the full-set start is a direct Cholesky solve (gram_dense_solve); bit 3: dilated sets for points 2 and 3
+  if (const char *e = getenv("DECAES_LC_HINTS")) P.lc_hints = atoi(e) & 15;  // bit 3: dilated sets for the second / third point
   // In-phase votes (voxel.cuh: cta_or): flip-angle probes and L-curve steps are uniform enough that keeping the warps
   // in step pays (cfg3: +20 %, cfg1: +13 %); the four initial L-curve points and the Brent searches vary too much between
   // voxels (-1 % / -6 %).  With few warps per SM (nT2 = 60: six) there is little instruction-cache pressure to relieve

@@ -54,6 +54,7 @@ struct PipeParams {
   int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too: 1 = all probes, 2 = all but the seed probes
   double kkt_tau;           // screening threshold of the polish: duals above -kkt_tau * max|c| are recomputed explicitly
   int fa_refine;            // iterative-refinement step on the flip-angle probes
+  int fa_rough_seeds;       // seed probes without refinement / polish; a seed that ends up in the final bracket is probed again precisely
   int step_sync;            // CTA-wide votes inside the phases (cta_or): bit 0 = before every flip-angle probe, bit 1 = at every step of the
                             // L-curve search, bit 2 = at its four initial points too, bit 3 = at every other regularised solve (Brent searches)
   int lc_hints;             // L-curve start hints: bit 0 = full column set at mu = e^2, bit 1 = flip-angle fit's set at mu = e^-8
@@ -146,7 +147,7 @@ struct Src {               // where the current basis of the Gram solver lives
 #define DECAES_RESID_CHUNK 4  // columns per L2 round trip of the explicit residual (8: +0.5 % on cfg3, -3 % on the nT2 = 60 configs)
 #endif
 #ifndef DECAES_EPG_UNROLL
-#define DECAES_EPG_UNROLL 1  // state loop of the shared-memory EPG (independent iterations: unrolling buys ILP, costs code)
+#define DECAES_EPG_UNROLL 2  // state loop of the shared-memory EPG (independent iterations: unrolling buys ILP, costs code; +1.3 % with two echoes per sweep)
 #endif
 #ifdef DECAES_PROFILE
 #define PROF_BEGIN(id) long long prof_t0_##id = clock64()
@@ -211,6 +212,7 @@ struct Warp {
   double *lc_pts_p, *lc_states_p, *slots_x_p, *fa_u_p, *fa_du_p;
   unsigned long long *fa_mask_p;
   double *bd, *sig, *fit, *slot_mu, *slot_lmu, *slot_r2, *slot_x2;
+  unsigned long long fa_rough = 0ull; // grid angles probed without refinement / polish so far
   double c_epg[2];                  // c = A'b of the fitted-angle basis, accumulated by the shared-memory EPG (one entry per pass)
   int solve_vote = 0;               // step_sync bit that makes the regularised solves vote right now (0: they do not)
   unsigned long long fa_mask_best;  // active set of the probed grid angle nearest to the fitted one (0 = none)
@@ -462,15 +464,19 @@ struct Warp {
     }
   }
 
-  __device__ void fa_probe(int I, unsigned long long &seen, int &numeval) {
+  // rough: solve without refinement and KKT polish (the loss is second-order accurate, its slope to ~cond^2 eps: good
+  // enough to steer the search, not to define the fitted angle)
+  __device__ void fa_probe(int I, unsigned long long &seen, int &numeval, bool rough = false) {
     double u, du;
     if (cP.step_sync & 1) cta_or(true);
-    if constexpr (GRAM) fa_eval_gram(I, u, du, seen);
+    if constexpr (GRAM) fa_eval_gram(I, u, du, seen, rough);
     else fa_eval(I, u, du);
     if (lane == 0) fa_u_p[I] = u, fa_du_p[I] = du;
     __syncwarp();
+    if (rough) fa_rough |= 1ull << I;
+    else fa_rough &= ~(1ull << I);
+    if (!((seen >> I) & 1ull)) numeval++;
     seen |= (1ull << I);
-    numeval++;
   }
 
   // DiscreteSurrogateSearcher + bisection_search  src/splines.jl:705-850 (D = 1).  The seed order
@@ -479,7 +485,8 @@ struct Warp {
     unsigned long long seen = 0ull;
     int numeval = 0;
     const int maxeval = cP.maxeval, nA = cP.nA;
-    for (int s = 0; s < cP.nseed; s++) fa_probe(cP.seeds[s], seen, numeval);
+    fa_rough = 0ull;
+    for (int s = 0; s < cP.nseed; s++) fa_probe(cP.seeds[s], seen, numeval, GRAM && !LEGACY && cP.fa_rough_seeds);
     double x, u;
     unsigned long long seen_sugg = 0ull;  // legacy: the scan is expensive, skip it when nothing new was probed
     if constexpr (LEGACY) suggest_point_legacy(seen, x, u), seen_sugg = seen;
@@ -512,6 +519,17 @@ struct Warp {
       if constexpr (!LEGACY) suggest_point(seen, x, u);
       else if (seen != seen_sugg) suggest_point_legacy(seen, x, u), seen_sugg = seen;
       if (numeval >= maxeval || (hi - lo) <= 1) {
+        if constexpr (GRAM && !LEGACY) {
+          // the fitted angle is the minimum of the Hermite piece over [lo, hi]: both ends must be precise.  A seed that
+          // was probed roughly is probed again (warm start from its own active set) and the search resumes from there.
+          const unsigned long long need = fa_rough & seen & ((1ull << lo) | (1ull << hi));
+          if (need) {
+            if ((need >> lo) & 1ull) fa_probe(lo, seen, numeval);
+            if (hi != lo && ((need >> hi) & 1ull)) fa_probe(hi, seen, numeval);
+            suggest_point(seen, x, u);
+            continue;
+          }
+        }
         if constexpr (GRAM) {
           // active set of the probed node nearest to the fitted angle: warm start of the first regularised solve
           int In = (fabs(cP.angles[lo] - x) <= fabs(cP.angles[hi] - x)) ? lo : hi;
@@ -959,7 +977,7 @@ struct Warp {
     // first point (mu = e^-8: practically the unregularised problem) starts from the flip-angle fit's active set,
     // the last one (mu = e^2) from the full column set
     solve_vote = 4;
-    for (int q = 0; q < 4; q++) si[q] = lc_eval(sx[q], npts, Asrc, q == 0 ? (cP.lc_hints & 2) : (q == 3 ? (cP.lc_hints & 1) : 0));
+    for (int q = 0; q < 4; q++) si[q] = lc_eval(sx[q], npts, Asrc, q == 0 ? (cP.lc_hints & 2) : (q == 3 ? (cP.lc_hints & 1) : ((cP.lc_hints & 8) ? q + 2 : 0)));
     const double tlx = pts[4 * si[0] + 1], tly = pts[4 * si[0] + 2], brx = pts[4 * si[3] + 1], bry = pts[4 * si[3] + 2];
     lc_update_curvature(sx, si, npts, tlx, tly, brx, bry, Ctol);
     int iter = 0;
@@ -1532,7 +1550,7 @@ struct Warp {
   }
 
   // loss_with_grad!  src/splines.jl:1010-1041 on grid angle k
-  __device__ __noinline__ void fa_eval_gram(int kang, double &u, double &du, unsigned long long seen) {
+  __device__ __noinline__ void fa_eval_gram(int kang, double &u, double &du, unsigned long long seen, bool rough = false) {
     const int lane = this->lane;
     VIEW(double, fit);
     VIEW(double, Gs);
@@ -1554,7 +1572,7 @@ struct Warp {
     // cold start needs pivots (measured: 17 inner iterations from 63 grid steps away, 7.5 cold, 4.4 from 1 step)
     unsigned long long warm = 0ull;
     if (seen && cP.fa_warm) {
-      unsigned long long below = seen & ((1ull << kang) - 1ull), above = seen >> kang;  // bit kang itself is never set
+      unsigned long long below = seen & ((1ull << kang) - 1ull), above = seen >> kang;  // (bit kang set: a second, precise probe of a seed - its own set)
       int jb = below ? 63 - __clzll((long long)below) : -1000;
       int ja = above ? kang + __ffsll((long long)above) - 1 : 1000;
       int jn = (kang - jb <= ja - kang) ? jb : ja;
@@ -1563,7 +1581,8 @@ struct Warp {
     GramOut o;
     // fa_polish = 0 leaves the KKT polish to the solves whose x is an output (+1.2 % throughput; one voxel in 2,048 of the
     // three-pool stress family then misses the flip-angle tolerance: 1.4e-6 instead of 3.4e-7)
-    u = gram_solve_unreg(src, o, warm, cP.fa_refine != 0, cP.fa_polish == 1 || (cP.fa_polish == 2 && __popcll(seen) >= cP.nseed));
+    u = gram_solve_unreg(src, o, warm, cP.fa_refine != 0 && !rough,
+                         !rough && (cP.fa_polish == 1 || (cP.fa_polish == 2 && __popcll(seen) >= cP.nseed)));
     if (lane == 0) fa_mask_p[kang] = o.mask;
     const double *dAk = cP.dbasis_cm + (size_t)kang * nTE * n;
     GL(dAk);
@@ -1679,7 +1698,7 @@ struct Warp {
 #pragma unroll
       for (int cq = 0; cq < 8; cq++) acc[cq][0] = acc[cq][1] = 0.0;
       const bool pv = 8 * cp + g < n;
-      _Pragma("unroll 1") for (int i0 = 0; i0 < nTE; i0 += 4) {
+      _Pragma("unroll 1") for (int i0 = 0; i0 < nTE; i0 += 4) {  // (unroll 4: four L2 round trips per tile row instead of fourteen, but 4.6x the code: -4 % on the nT2 = 60 configs, nothing on cfg3)
         const bool iv = i0 + t < nTE;
         const double *row = Arm + (iv ? i0 + t : 0) * rs + g * cs;
         const int c8 = 8 * cs;
@@ -1749,8 +1768,16 @@ struct Warp {
       const int nearest = warp_argmin_bits(key, lane, best);
       if (best != ~0ull) {
         const double *sx = slots_x_p + nearest * n;
-        _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = sx[j];
-        wmask = slot_mask[nearest];
+        const unsigned long long m0 = slot_mask[nearest];
+        wmask = m0;
+        if (hint >= 3) {
+          // second / third L-curve point (mu = e^-4.2, e^-1.8): the active set widens around the peaks it already has; start
+          // from the inherited set dilated by hint - 2 columns (oracle: 2.7 instead of 3.8, 4.0 instead of 8.3 set changes)
+          _Pragma("unroll 1") for (int d = 0; d < hint - 2; d++) wmask |= (wmask << 1) | (wmask >> 1);
+          if (n < 64) wmask &= (1ull << n) - 1ull;
+        }
+        // (the new columns start at a small positive value: a feasible interior point, so a wrong guess leaves alone)
+        _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = ((m0 >> j) & 1ull) ? sx[j] : (((wmask >> j) & 1ull) ? 1e-3 : 0.0);
         __syncwarp();
       }
     }

@@ -142,6 +142,27 @@ def test_set_flip_angle_and_b1_map(pkg, orc):
     rep = parity.compare(ref, got)
     assert rep["frac_out_of_tolerance_same_mu"] <= 0.02 and rep["mu_flip_frac"] <= 0.08, rep
 
+@pytest.mark.parametrize("Reg", ["gcv", "lcurve"])
+def test_fixed_angle_and_b1_map_with_gcv_and_lcurve(pkg, orc, Reg):
+    """The round-2 call sites that only these option combinations reach: the shared-memory singular values of Reg = gcv
+    from the grid tables (SetFlipAngle) and from the voxel's own basis (B1 map, RefConAngle != 180), and the L-curve
+    steps kept in step by CTA votes when there is no flip-angle phase to vote in."""
+    nvox, nTE, nT2, TE = 384, 32, 40, 10e-3
+    img = orc.mock_image(nvox, nTE, TE, seed=21)
+    cases = [dict(SetFlipAngle=165.0), dict(alpha_provided=True), dict(alpha_provided=True, RefConAngle=150.0)]
+    b1 = np.linspace(128.0, 179.0, nvox)
+    for kw in cases:
+        o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, TE, Reg=Reg, ngpus=1, **kw)
+        init = b1 if kw.get("alpha_provided") else None
+        ref, _ = orc.t2map(img, o, alpha_init=init)
+        alt, _ = orc.t2map(img, o, alpha_init=init, L=orc.lib_variant("simd"))
+        got = gpu_t2map(pkg, orc, img, o, None, alpha_init=init)
+        rep, own = parity.compare(ref, got), parity.compare(ref, alt)["mu_flip_frac"]
+        assert rep["nan_mismatch"] == 0 and rep["out_of_tolerance_same_mu"] <= 1, (Reg, kw, rep)
+        assert rep["mu_flip_frac"] <= parity.flip_bound(own, nvox) + 0.005, (Reg, kw, own, rep)
+        st = pkg.last_stats()
+        assert st["lcurve_overflow"] == 0 and st["nnls_itercap"] == 0, st
+
 
 @pytest.mark.parametrize("beta,Reg", [(150.0, "none"), (120.0, "lcurve"), (165.0, "chi2")])
 def test_refcon_angle(pkg, orc, beta, Reg):
