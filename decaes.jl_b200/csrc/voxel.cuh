@@ -466,7 +466,7 @@ struct Warp {
 
   // rough: solve without refinement and KKT polish (the loss is second-order accurate, its slope to ~cond^2 eps: good
   // enough to steer the search, not to define the fitted angle)
-  __device__ void fa_probe(int I, unsigned long long &seen, int &numeval, bool rough = false) {
+  __device__ __noinline__ void fa_probe(int I, unsigned long long &seen, int &numeval, bool rough = false) {
     double u, du;
     if (cP.step_sync & 1) cta_or(true);
     if constexpr (GRAM) fa_eval_gram(I, u, du, seen, rough);
@@ -486,7 +486,11 @@ struct Warp {
     int numeval = 0;
     const int maxeval = cP.maxeval, nA = cP.nA;
     fa_rough = 0ull;
+#ifdef DECAES_FA_ROUGH
     for (int s = 0; s < cP.nseed; s++) fa_probe(cP.seeds[s], seen, numeval, GRAM && !LEGACY && cP.fa_rough_seeds);
+#else
+    _Pragma("unroll 1") for (int s = 0; s < cP.nseed; s++) fa_probe(cP.seeds[s], seen, numeval);
+#endif
     double x, u;
     unsigned long long seen_sugg = 0ull;  // legacy: the scan is expensive, skip it when nothing new was probed
     if constexpr (LEGACY) suggest_point_legacy(seen, x, u), seen_sugg = seen;
@@ -519,6 +523,7 @@ struct Warp {
       if constexpr (!LEGACY) suggest_point(seen, x, u);
       else if (seen != seen_sugg) suggest_point_legacy(seen, x, u), seen_sugg = seen;
       if (numeval >= maxeval || (hi - lo) <= 1) {
+#ifdef DECAES_FA_ROUGH  // rejected experiment (see PipeParams::fa_rough_seeds), kept out of the shipped kernel
         if constexpr (GRAM && !LEGACY) {
           // the fitted angle is the minimum of the Hermite piece over [lo, hi]: both ends must be precise.  A seed that
           // was probed roughly is probed again (warm start from its own active set) and the search resumes from there.
@@ -530,6 +535,7 @@ struct Warp {
             continue;
           }
         }
+#endif
         if constexpr (GRAM) {
           // active set of the probed node nearest to the fitted angle: warm start of the first regularised solve
           int In = (fabs(cP.angles[lo] - x) <= fabs(cP.angles[hi] - x)) ? lo : hi;
@@ -1398,23 +1404,23 @@ struct Warp {
     const int nTE = cP.nTE;
     double *T = Gs;
     const int ld = cP.ldg;
-    // g_t = A[:,P[t]]' r - mu2 s_t: lane <-> echo (coalesced L2 reads, all lanes busy), two columns per round
-    _Pragma("unroll 1") for (int t = 0; t < k; t += 2) {
-      const int t1c = t + 1 < k ? t + 1 : t;
-      const double *c0 = Acm + gws.P[t] * nTE, *c1 = Acm + gws.P[t1c] * nTE;
-      double a0 = 0.0, a1 = 0.0;
-      _Pragma("unroll 2") for (int i = lane; i < nTE; i += 32) {
-        const double ri = fit[i];
-        a0 = fma(c0[i], ri, a0), a1 = fma(c1[i], ri, a1);
+    // g_t = A[:,P[t]]' r - mu2 s_t: lane <-> echo (coalesced L2 reads), four columns per L2 round trip, sums through the
+    // shared out-of-line butterfly (the kernel pays for code size: 463 -> ~300 instructions, same arithmetic)
+    const int i0 = lane < nTE ? lane : 0, i1 = lane + 32 < nTE ? lane + 32 : i0, i2 = lane + 64 < nTE ? lane + 64 : i0;
+    const double r0 = lane < nTE ? fit[i0] : 0.0, r1 = lane + 32 < nTE ? fit[i1] : 0.0, r2 = lane + 64 < nTE ? fit[i2] : 0.0;
+    _Pragma("unroll 1") for (int tb = 0; tb < k; tb += 4) {
+      double v0[4], v1[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const double *col = Acm + gws.P[tb + u < k ? tb + u : tb] * nTE;
+        v0[u] = col[i0], v1[u] = col[i1];
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(DECAES_FULL_MASK, a0, o);
-        a1 += __shfl_xor_sync(DECAES_FULL_MASK, a1, o);
-      }
-      if (lane == 0) {
-        gws.t1[t] = fma(-mu2, gws.s[t], a0);
-        if (t + 1 < k) gws.t1[t + 1] = fma(-mu2, gws.s[t + 1], a1);
+      for (int u = 0; u < 4; u++) {
+        double a = fma(v1[u], r1, __dmul_rn(v0[u], r0));
+        if (nTE > 64) a = fma(Acm[gws.P[tb + u < k ? tb + u : tb] * nTE + i2], r2, a);
+        a = warp_sum(a);
+        if (lane == 0 && tb + u < k) gws.t1[tb + u] = fma(-mu2, gws.s[tb + u], a);
       }
     }
     __syncwarp();
