@@ -194,7 +194,7 @@ def parity_block(pkg, orc, wl, nvox, seed):
             "tolerances": "dist rel 1e-6 / abs 1e-9; alpha, MWF, gmT2 abs 1e-6",
             "out_of_tolerance": rep["voxels_out_of_tolerance"], "out_of_tolerance_same_mu": rep["out_of_tolerance_same_mu"],
             "mu_flips": rep["mu_flips"], "mu_flip_frac": rep["mu_flip_frac"], "mu_flip_median_dlog": rep["mu_flip_median_dlog"],
-            "mu_flips_between_two_cpu_builds": own["mu_flips"], "support_diff": rep["support_diff"],
+            "mu_flips_between_two_cpu_builds": own["mu_flips"], "support_diff": rep["support_diff"], "support_diff_same_mu": rep["support_diff_same_mu"],
             "alpha_max_abs": rep["alpha_max_abs"], "sfr_max_abs": rep["sfr_max_abs"],
             "early_returns": st["early_returns"], "early_returns_oracle": int(ost.early_returns),
             "lcurve_overflow": st["lcurve_overflow"], "nnls_itercap": st["nnls_itercap"]}

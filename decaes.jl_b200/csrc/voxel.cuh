@@ -49,7 +49,8 @@ struct PipeParams {
   int epg_smem;             // EPG at the fitted angle keeps its states in shared memory (lane <-> component)
   int epg_fuse;             // shared-memory EPG: two echoes per sweep over the states
   int need_rm;              // the voxel's basis is also kept row-major in the global scratch (0: column-major only, c = A'b comes out of the EPG)
-  int gcv_smem;             // Reg = gcv: the singular values are computed in shared memory during the basis phase (gcv_svdvals_smem)
+  int gcv_smem;             // Reg = gcv: the singular values are computed in shared memory during the basis phase (2: bidiagonalisation +
+                            // bisection, gcv_svdvals_bidiag; 1: parallel one-sided Jacobi, gcv_svdvals_smem; 0: global-memory Jacobi)
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
   int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too: 1 = all probes, 2 = all but the seed probes
   double kkt_tau;           // screening threshold of the polish: duals above -kkt_tau * max|c| are recomputed explicitly
@@ -448,7 +449,7 @@ struct Warp {
       const bool rm = cP.need_rm != 0;
       const double *Ab = rm ? g + sl.pristine : g + sl.pristine_cm;
       const int rs = rm ? cP.ld : 1, cs = rm ? 1 : cP.nTE;
-      if (cP.reg == 2 && cP.gcv_smem) gcv_svdvals_smem(Ab, rs, cs, V);
+      if (cP.reg == 2 && cP.gcv_smem) gcv_svd_shared(Ab, rs, cs, V);
       if (!rm && cP.epg_smem) {  // right-hand side c = A'b straight from the EPG's registers
         const int LW = cP.epg_lanes;
         if (lane < LW && lane < cP.nT2) cvec[lane] = c_epg[0];
@@ -1263,6 +1264,142 @@ struct Warp {
     __syncwarp();
   }
 
+  // Singular values for Reg = gcv, third version (PipeParams::gcv_smem == 2): Golub-Kahan Householder bidiagonalisation of the
+  // tall r x c copy in shared memory (4 r c^2 / 3 flops instead of ~10 Jacobi sweeps of 6 r c^2 each), then bisection on the
+  // Sturm counts of the Golub-Kahan tridiagonal form of the bidiagonal (order 2c, zero diagonal, off-diagonals d1 e1 d2 e2 ...:
+  // its eigenvalues are -sigma_c .. -sigma_1, sigma_1 .. sigma_c).  This is the route LAPACK takes as well (dgebrd + a bidiagonal
+  // solver; the reference's dgesdd_, src/utils.jl:103-134): backward stable, every sigma to a few eps * sigma_max.
+  //  * left reflector k (column k, rows k..r-1): lane <-> column j > k, the reflector is read as a broadcast;
+  //  * right reflector k (row k, columns k+1..c-1): lane <-> row i > k; the leading dimension c | 1 is odd, so both
+  //    access directions are free of bank conflicts; two columns / rows per lane advance together;
+  //  * bisection: lane <-> singular values lane and lane + 32, all lanes take the same 54 halvings of [0, ||B||_F]
+  //    (interval 6e-17 ||B||_F), one reciprocal + one fma per off-diagonal entry and chain.
+  __device__ __noinline__ void gcv_svdvals_bidiag(const double *Asrc, int rs, int cs, double *B) {  // element (i, j) at i * rs + j * cs
+    SH(B);
+    GL(Asrc);
+    const int lane = this->lane;
+    const int m = cP.nTE, n = cP.nT2;
+    const int R = m >= n ? m : n, C = m >= n ? n : m, ld = C | 1;
+    _Pragma("unroll 1") for (int k = lane; k < m * n; k += 32) {
+      int i, j;  // in the order the source is laid out
+      if (rs == 1) j = k / m, i = k - j * m;
+      else i = k / n, j = k - i * n;
+      const double v = Asrc[i * rs + j * cs];
+      if (m >= n) B[i * ld + j] = v;
+      else B[j * ld + i] = v;
+    }
+    __syncwarp();
+    _Pragma("unroll 1") for (int k = 0; k < C; k++) {
+      {  // left reflector: annihilate B[k+1:R, k]
+        double *const colk = B + k;
+        double acc = 0.0;
+        _Pragma("unroll 1") for (int i = k + 1 + lane; i < R; i += 32) acc = fma(colk[i * ld], colk[i * ld], acc);
+        const double xn2 = warp_sum(acc), x0 = colk[k * ld];
+        if (xn2 != 0.0) {  // (warp-uniform: the butterfly sum is bitwise identical on every lane)
+          const double beta = -copysign(sqrt(fma(x0, x0, xn2)), x0);
+          const double tau = (beta - x0) / beta, sc = 1.0 / (x0 - beta);
+          _Pragma("unroll 1") for (int i = k + 1 + lane; i < R; i += 32) colk[i * ld] *= sc;
+          __syncwarp();
+          if (lane == 0) colk[k * ld] = beta;
+          const int j0 = k + 1 + lane, j1 = j0 + 32;
+          if (j0 < C) {
+            const bool two = j1 < C;
+            double *const c0 = B + j0, *const c1 = B + (two ? j1 : j0);
+            double w0 = c0[k * ld], w1 = c1[k * ld];
+            _Pragma("unroll 2") for (int i = k + 1; i < R; i++) {
+              const double vi = colk[i * ld];
+              w0 = fma(vi, c0[i * ld], w0), w1 = fma(vi, c1[i * ld], w1);
+            }
+            w0 *= tau, w1 *= tau;
+            c0[k * ld] -= w0;
+            if (two) c1[k * ld] -= w1;
+            _Pragma("unroll 2") for (int i = k + 1; i < R; i++) {
+              const double vi = colk[i * ld];
+              c0[i * ld] = fma(-vi, w0, c0[i * ld]);
+              if (two) c1[i * ld] = fma(-vi, w1, c1[i * ld]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (k < C - 2) {  // right reflector: annihilate B[k, k+2:C]
+        double *const rowk = B + k * ld;
+        double acc = 0.0;
+        _Pragma("unroll 1") for (int j = k + 2 + lane; j < C; j += 32) acc = fma(rowk[j], rowk[j], acc);
+        const double xn2 = warp_sum(acc), x0 = rowk[k + 1];
+        if (xn2 != 0.0) {
+          const double beta = -copysign(sqrt(fma(x0, x0, xn2)), x0);
+          const double tau = (beta - x0) / beta, sc = 1.0 / (x0 - beta);
+          _Pragma("unroll 1") for (int j = k + 2 + lane; j < C; j += 32) rowk[j] *= sc;
+          __syncwarp();
+          if (lane == 0) rowk[k + 1] = beta;
+          _Pragma("unroll 1") for (int i0 = k + 1 + lane; i0 < R; i0 += 64) {
+            const bool two = i0 + 32 < R;
+            double *const r0 = B + i0 * ld, *const r1 = B + (two ? i0 + 32 : i0) * ld;
+            double z0 = r0[k + 1], z1 = r1[k + 1];
+            _Pragma("unroll 2") for (int j = k + 2; j < C; j++) {
+              const double uj = rowk[j];
+              z0 = fma(r0[j], uj, z0), z1 = fma(r1[j], uj, z1);
+            }
+            z0 *= tau, z1 *= tau;
+            r0[k + 1] -= z0;
+            if (two) r1[k + 1] -= z1;
+            _Pragma("unroll 2") for (int j = k + 2; j < C; j++) {
+              const double uj = rowk[j];
+              r0[j] = fma(-z0, uj, r0[j]);
+              if (two) r1[j] = fma(-z1, uj, r1[j]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    // squares of the off-diagonals of the Golub-Kahan form, b = (d_0, e_0, d_1, ..., d_{C-1}), at the start of B
+    const int nb = 2 * C - 1;
+    double bq[4], fro = 0.0, mx = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int t = lane + 32 * u, kk = t >> 1;
+      double bt = 0.0;
+      if (t < nb) bt = B[kk * ld + kk + (t & 1)];
+      bq[u] = __dmul_rn(bt, bt);
+      fro += bq[u], mx = fmax(mx, bq[u]);
+    }
+    fro = warp_sum(fro), mx = warp_max(mx);
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (lane + 32 * u < nb) B[lane + 32 * u] = bq[u];
+    __syncwarp();
+    const double bound = sqrt(fro) * 1.0000001, pivmin = DBL_MIN * fmax(1.0, mx);
+    double lo0 = 0.0, hi0 = bound, lo1 = 0.0, hi1 = bound;
+    const int t0 = C + lane, t1 = C + lane + 32;  // sigma_j (ascending, 0-based) < x  <=>  #(eigenvalues < x) > C + j
+    _Pragma("unroll 1") for (int it = 0; it < 54; it++) {
+      const double x0 = (lo0 + hi0) / 2, x1 = (lo1 + hi1) / 2;
+      double q0 = -x0, q1 = -x1;
+      int c0 = 1, c1 = 1;
+      _Pragma("unroll 2") for (int i = 0; i < nb; i++) {
+        const double bb = B[i];
+        if (fabs(q0) < pivmin) q0 = -pivmin;
+        if (fabs(q1) < pivmin) q1 = -pivmin;
+        q0 = fma(-bb, __drcp_rn(q0), -x0), q1 = fma(-bb, __drcp_rn(q1), -x1);
+        c0 += q0 < 0.0, c1 += q1 < 0.0;
+      }
+      if (c0 > t0) hi0 = x0; else lo0 = x0;
+      if (c1 > t1) hi1 = x1; else lo1 = x1;
+    }
+    double *gam = g + sl.gcv_gamma;
+    GL(gam);
+    if (lane < C) gam[lane] = (lo0 + hi0) / 2;
+    if (lane + 32 < C) gam[lane + 32] = (lo1 + hi1) / 2;
+    __threadfence_block();
+    __syncwarp();
+  }
+  __device__ __forceinline__ void gcv_svd_shared(const double *Asrc, int rs, int cs, double *B) {
+    if (cP.gcv_smem == 2) gcv_svdvals_bidiag(Asrc, rs, cs, B);
+    else gcv_svdvals_smem(Asrc, rs, cs, B);
+  }
+
   __device__ __noinline__ double gcv_fun(double logmu, const double *Asrc) {  // log(max(gcv, eps^2/m))  :1150-1154, 1213-1229
     const int m = cP.nTE, n = cP.nT2;
     double mu = exp(logmu);
@@ -1869,7 +2006,7 @@ struct Warp {
     if (cP.fixed_alpha && !cP.alpha_provided) {
       if constexpr (GRAM) {
         cursrc.G = cP.gram_set, cursrc.ldg = cP.ldg, cursrc.Arm = cP.basis_rm, cursrc.Acm = cP.basis_cm;
-        if (cP.reg == 2 && cP.gcv_smem) gcv_svdvals_smem(cP.basis_rm, cP.ld, 1, V);
+        if (cP.reg == 2 && cP.gcv_smem) gcv_svd_shared(cP.basis_rm, cP.ld, 1, V);
         stage_bulk(Gs, cP.gram_set, (unsigned)(cP.a_elems * 8));
         gram_rhs(cursrc.Arm);
       }

@@ -60,10 +60,12 @@ def compare(ref, got, scalars=("alpha", "sfr", "ggm"), extra=("gdn", "gva", "fnr
         rep["mu_flip_frac"] = float(flip.mean()) if nvox else 0.0
         rep["mu_flip_median_dlog"] = float(np.nanmedian(dlog[flip])) if flip.any() else 0.0
         rep["mu_flip_max_dlog"] = float(np.nanmax(dlog[flip])) if flip.any() else 0.0
+        rep["support_diff_same_mu"] = int((support_diff & ~flip).sum())  # (a voxel at another mu may well have another support)
         rep["out_of_tolerance_same_mu"] = int((fails & ~flip).sum())
         rep["frac_out_of_tolerance_same_mu"] = float((fails & ~flip).mean()) if nvox else 0.0
     else:
         rep["mu_flips"], rep["mu_flip_frac"] = 0, 0.0
+        rep["support_diff_same_mu"] = rep["support_diff"]
         rep["out_of_tolerance_same_mu"] = rep["voxels_out_of_tolerance"]
         rep["frac_out_of_tolerance_same_mu"] = rep["frac_out_of_tolerance"]
     return rep

@@ -59,7 +59,7 @@ def test_gpu_matches_oracle(pkg, orc, name, nTE, TE, nT2, Reg, extra, part_kw, n
     print(name, rep, "oracle early returns:", st.early_returns, "two-CPU-builds flip rate:", own)
     assert rep["nan_mismatch"] == 0
     # every voxel that selected the same regularisation parameter meets the north_star tolerances ...
-    assert rep["frac_out_of_tolerance_same_mu"] <= maxfrac and rep["support_diff"] == 0, rep
+    assert rep["frac_out_of_tolerance_same_mu"] <= maxfrac and rep["support_diff_same_mu"] == 0, rep
     # ... and the mu searches (chaotic at their 1e-4 termination width, tests/test_oracle_sensitivity.py) do not flip
     # more often than two CPU builds of the same algorithm do on these very voxels
     assert rep["mu_flip_frac"] <= flip_bound(own, nvox), (own, rep)
