@@ -51,6 +51,7 @@ struct PipeParams {
   int need_rm;              // the voxel's basis is also kept row-major in the global scratch (0: column-major only, c = A'b comes out of the EPG)
   int gcv_smem;             // Reg = gcv: the singular values are computed in shared memory during the basis phase (2: bidiagonalisation +
                             // bisection, gcv_svdvals_bidiag; 1: parallel one-sided Jacobi, gcv_svdvals_smem; 0: global-memory Jacobi)
+  int gcv_sturm2;           // bisection of gcv_svdvals_bidiag: two Sturm pivots per reciprocal
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
   int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too: 1 = all probes, 2 = all but the seed probes
   double kkt_tau;           // screening threshold of the polish: duals above -kkt_tau * max|c| are recomputed explicitly
@@ -225,6 +226,7 @@ struct Warp {
   int cur_slot;     // 0-based current cache slot (persists across voxels like work.idx[])
   int lane;
   unsigned long long n_early, n_overflow, n_itercap, n_polish;
+  bool gcv_fixed_done = false;             // Reg = gcv with SetFlipAngle: singular values of the one basis already computed by this warp
   int nsolve_voxel = 0, nunreg_voxel = 0;  // Tikhonov / unregularised solves of the current voxel (DECAES_PROFILE)
 
   __device__ Warp(const PipeParams &p, double *smem, double *gscratch)
@@ -1274,21 +1276,48 @@ struct Warp {
   //    access directions are free of bank conflicts; two columns / rows per lane advance together;
   //  * bisection: lane <-> singular values lane and lane + 32, all lanes take the same 54 halvings of [0, ||B||_F]
   //    (interval 6e-17 ||B||_F), one reciprocal + one fma per off-diagonal entry and chain.
+  // 1 / a for finite, normal |a| in [1e-150, 1e150] (the clamped Sturm pivots): the hardware seed (MUFU.RCP64H, ~20 bits) and
+  // one cubic Newton step, 2^-60 relative - no range checks and no slow-path branch, so independent chains interleave
+  static __device__ __forceinline__ double rcp_nr(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    e = fma(e, e, e);
+    return fma(x, e, x);
+  }
   __device__ __noinline__ void gcv_svdvals_bidiag(const double *Asrc, int rs, int cs, double *B) {  // element (i, j) at i * rs + j * cs
     SH(B);
     GL(Asrc);
     const int lane = this->lane;
     const int m = cP.nTE, n = cP.nT2;
     const int R = m >= n ? m : n, C = m >= n ? n : m, ld = C | 1;
-    _Pragma("unroll 1") for (int k = lane; k < m * n; k += 32) {
-      int i, j;  // in the order the source is laid out
-      if (rs == 1) j = k / m, i = k - j * m;
-      else i = k / n, j = k - i * n;
-      const double v = Asrc[i * rs + j * cs];
-      if (m >= n) B[i * ld + j] = v;
-      else B[j * ld + i] = v;
+    {
+      // copy in the order the source is laid out (inner extent w: column-major m, row-major n), four loads in flight;
+      // the (outer, inner) position advances by 32 without a division
+      const bool cmaj = rs == 1;
+      const int w = cmaj ? m : n, tot = m * n;
+      int in = lane % w, out = lane / w;
+      _Pragma("unroll 1") for (int k0 = lane; k0 < tot; k0 += 128) {
+        double v[4];
+        int dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const bool ok = k0 + 32 * u < tot;
+          const int i = cmaj ? in : out, j = cmaj ? out : in;
+          v[u] = ok ? Asrc[i * rs + j * cs] : 0.0;
+          dst[u] = ok ? (m >= n ? i * ld + j : j * ld + i) : -1;
+          in += 32;
+          while (in >= w) in -= w, out++;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (dst[u] >= 0) B[dst[u]] = v[u];
+      }
     }
     __syncwarp();
+    // Reflectors are kept unnormalised: v = x - beta e_1 with beta = -sign(x_0) ||x||, H = I - g v v', g = 1 / (||x|| (||x|| + |x_0|));
+    // v_0 lives in a register, the rest of v stays where x was.  The update loops load a chunk of four rows / columns before
+    // they store it (the compiler cannot see that the reflector and the updated entries never overlap).
     _Pragma("unroll 1") for (int k = 0; k < C; k++) {
       {  // left reflector: annihilate B[k+1:R, k]
         double *const colk = B + k;
@@ -1296,24 +1325,39 @@ struct Warp {
         _Pragma("unroll 1") for (int i = k + 1 + lane; i < R; i += 32) acc = fma(colk[i * ld], colk[i * ld], acc);
         const double xn2 = warp_sum(acc), x0 = colk[k * ld];
         if (xn2 != 0.0) {  // (warp-uniform: the butterfly sum is bitwise identical on every lane)
-          const double beta = -copysign(sqrt(fma(x0, x0, xn2)), x0);
-          const double tau = (beta - x0) / beta, sc = 1.0 / (x0 - beta);
-          _Pragma("unroll 1") for (int i = k + 1 + lane; i < R; i += 32) colk[i * ld] *= sc;
+          const double nrm = sqrt(fma(x0, x0, xn2));
+          const double v0 = x0 + copysign(nrm, x0), g = 1.0 / (nrm * (nrm + fabs(x0)));
           __syncwarp();
-          if (lane == 0) colk[k * ld] = beta;
+          if (lane == 0) colk[k * ld] = -copysign(nrm, x0);
           const int j0 = k + 1 + lane, j1 = j0 + 32;
           if (j0 < C) {
             const bool two = j1 < C;
             double *const c0 = B + j0, *const c1 = B + (two ? j1 : j0);
-            double w0 = c0[k * ld], w1 = c1[k * ld];
-            _Pragma("unroll 2") for (int i = k + 1; i < R; i++) {
-              const double vi = colk[i * ld];
-              w0 = fma(vi, c0[i * ld], w0), w1 = fma(vi, c1[i * ld], w1);
+            double w0 = v0 * c0[k * ld], w1 = v0 * c1[k * ld];
+            int i = k + 1;
+            _Pragma("unroll 1") for (; i + 4 <= R; i += 4) {
+              double vv[4], a0[4], a1[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) vv[u] = colk[(i + u) * ld], a0[u] = c0[(i + u) * ld], a1[u] = c1[(i + u) * ld];
+#pragma unroll
+              for (int u = 0; u < 4; u++) w0 = fma(vv[u], a0[u], w0), w1 = fma(vv[u], a1[u], w1);
             }
-            w0 *= tau, w1 *= tau;
-            c0[k * ld] -= w0;
-            if (two) c1[k * ld] -= w1;
-            _Pragma("unroll 2") for (int i = k + 1; i < R; i++) {
+            _Pragma("unroll 1") for (; i < R; i++) w0 = fma(colk[i * ld], c0[i * ld], w0), w1 = fma(colk[i * ld], c1[i * ld], w1);
+            w0 *= g, w1 *= g;
+            c0[k * ld] = fma(-v0, w0, c0[k * ld]);
+            if (two) c1[k * ld] = fma(-v0, w1, c1[k * ld]);
+            i = k + 1;
+            _Pragma("unroll 1") for (; i + 4 <= R; i += 4) {
+              double vv[4], a0[4], a1[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) vv[u] = colk[(i + u) * ld], a0[u] = c0[(i + u) * ld], a1[u] = c1[(i + u) * ld];
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                c0[(i + u) * ld] = fma(-vv[u], w0, a0[u]);
+                if (two) c1[(i + u) * ld] = fma(-vv[u], w1, a1[u]);
+              }
+            }
+            _Pragma("unroll 1") for (; i < R; i++) {
               const double vi = colk[i * ld];
               c0[i * ld] = fma(-vi, w0, c0[i * ld]);
               if (two) c1[i * ld] = fma(-vi, w1, c1[i * ld]);
@@ -1328,23 +1372,38 @@ struct Warp {
         _Pragma("unroll 1") for (int j = k + 2 + lane; j < C; j += 32) acc = fma(rowk[j], rowk[j], acc);
         const double xn2 = warp_sum(acc), x0 = rowk[k + 1];
         if (xn2 != 0.0) {
-          const double beta = -copysign(sqrt(fma(x0, x0, xn2)), x0);
-          const double tau = (beta - x0) / beta, sc = 1.0 / (x0 - beta);
-          _Pragma("unroll 1") for (int j = k + 2 + lane; j < C; j += 32) rowk[j] *= sc;
+          const double nrm = sqrt(fma(x0, x0, xn2));
+          const double u0 = x0 + copysign(nrm, x0), g = 1.0 / (nrm * (nrm + fabs(x0)));
           __syncwarp();
-          if (lane == 0) rowk[k + 1] = beta;
+          if (lane == 0) rowk[k + 1] = -copysign(nrm, x0);
           _Pragma("unroll 1") for (int i0 = k + 1 + lane; i0 < R; i0 += 64) {
             const bool two = i0 + 32 < R;
             double *const r0 = B + i0 * ld, *const r1 = B + (two ? i0 + 32 : i0) * ld;
-            double z0 = r0[k + 1], z1 = r1[k + 1];
-            _Pragma("unroll 2") for (int j = k + 2; j < C; j++) {
-              const double uj = rowk[j];
-              z0 = fma(r0[j], uj, z0), z1 = fma(r1[j], uj, z1);
+            double z0 = u0 * r0[k + 1], z1 = u0 * r1[k + 1];
+            int j = k + 2;
+            _Pragma("unroll 1") for (; j + 4 <= C; j += 4) {
+              double uu[4], a0[4], a1[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) uu[u] = rowk[j + u], a0[u] = r0[j + u], a1[u] = r1[j + u];
+#pragma unroll
+              for (int u = 0; u < 4; u++) z0 = fma(a0[u], uu[u], z0), z1 = fma(a1[u], uu[u], z1);
             }
-            z0 *= tau, z1 *= tau;
-            r0[k + 1] -= z0;
-            if (two) r1[k + 1] -= z1;
-            _Pragma("unroll 2") for (int j = k + 2; j < C; j++) {
+            _Pragma("unroll 1") for (; j < C; j++) z0 = fma(r0[j], rowk[j], z0), z1 = fma(r1[j], rowk[j], z1);
+            z0 *= g, z1 *= g;
+            r0[k + 1] = fma(-u0, z0, r0[k + 1]);
+            if (two) r1[k + 1] = fma(-u0, z1, r1[k + 1]);
+            j = k + 2;
+            _Pragma("unroll 1") for (; j + 4 <= C; j += 4) {
+              double uu[4], a0[4], a1[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) uu[u] = rowk[j + u], a0[u] = r0[j + u], a1[u] = r1[j + u];
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                r0[j + u] = fma(-z0, uu[u], a0[u]);
+                if (two) r1[j + u] = fma(-z1, uu[u], a1[u]);
+              }
+            }
+            _Pragma("unroll 1") for (; j < C; j++) {
               const double uj = rowk[j];
               r0[j] = fma(-z0, uj, r0[j]);
               if (two) r1[j] = fma(-z1, uj, r1[j]);
@@ -1371,19 +1430,40 @@ struct Warp {
     for (int u = 0; u < 4; u++)
       if (lane + 32 * u < nb) B[lane + 32 * u] = bq[u];
     __syncwarp();
-    const double bound = sqrt(fro) * 1.0000001, pivmin = DBL_MIN * fmax(1.0, mx);
+    // pivots below pivmin in magnitude are replaced by -pivmin (LAPACK dlaebz's safeguard; an absolute perturbation of 1e-150)
+    const double bound = sqrt(fro) * 1.0000001, pivmin = 1e-150 * fmax(1.0, mx);
     double lo0 = 0.0, hi0 = bound, lo1 = 0.0, hi1 = bound;
     const int t0 = C + lane, t1 = C + lane + 32;  // sigma_j (ascending, 0-based) < x  <=>  #(eigenvalues < x) > C + j
+    const bool pairs = cP.gcv_sturm2 != 0;
     _Pragma("unroll 1") for (int it = 0; it < 54; it++) {
       const double x0 = (lo0 + hi0) / 2, x1 = (lo1 + hi1) / 2;
-      double q0 = -x0, q1 = -x1;
+      double q0 = -x0, q1 = -x1;  // first pivot: negative (x > 0)
       int c0 = 1, c1 = 1;
-      _Pragma("unroll 2") for (int i = 0; i < nb; i++) {
-        const double bb = B[i];
-        if (fabs(q0) < pivmin) q0 = -pivmin;
-        if (fabs(q1) < pivmin) q1 = -pivmin;
-        q0 = fma(-bb, __drcp_rn(q0), -x0), q1 = fma(-bb, __drcp_rn(q1), -x1);
+      if (pairs) {
+        // two pivots per reciprocal: with num = q_{i-1} q_i = -x q_{i-1} - b_i,  q_{i+1} = -x - b_{i+1} q_{i-1} / num and
+        // sign(q_i) = sign(num) sign(q_{i-1}); nb is odd, so the last entry takes a single step
+        _Pragma("unroll 1") for (int i = 0; i + 1 < nb; i += 2) {
+          const double ba = B[i], bb = B[i + 1];
+          double n0 = fma(-x0, q0, -ba), n1 = fma(-x1, q1, -ba);
+          if (fabs(n0) < pivmin * fabs(q0)) n0 = -pivmin * q0;  // q_i := -pivmin
+          if (fabs(n1) < pivmin * fabs(q1)) n1 = -pivmin * q1;
+          c0 += (n0 < 0.0) != (q0 < 0.0), c1 += (n1 < 0.0) != (q1 < 0.0);
+          q0 = fma(-__dmul_rn(bb, q0), rcp_nr(n0), -x0), q1 = fma(-__dmul_rn(bb, q1), rcp_nr(n1), -x1);
+          if (fabs(q0) < pivmin) q0 = -pivmin;
+          if (fabs(q1) < pivmin) q1 = -pivmin;
+          c0 += q0 < 0.0, c1 += q1 < 0.0;
+        }
+        const double bl = B[nb - 1];
+        q0 = fma(-bl, rcp_nr(q0), -x0), q1 = fma(-bl, rcp_nr(q1), -x1);
         c0 += q0 < 0.0, c1 += q1 < 0.0;
+      } else {
+        _Pragma("unroll 2") for (int i = 0; i < nb; i++) {
+          const double bb = B[i];
+          q0 = fma(-bb, __drcp_rn(q0), -x0), q1 = fma(-bb, __drcp_rn(q1), -x1);
+          if (fabs(q0) < pivmin) q0 = -pivmin;
+          if (fabs(q1) < pivmin) q1 = -pivmin;
+          c0 += q0 < 0.0, c1 += q1 < 0.0;
+        }
       }
       if (c0 > t0) hi0 = x0; else lo0 = x0;
       if (c1 > t1) hi1 = x1; else lo1 = x1;
@@ -2006,7 +2086,8 @@ struct Warp {
     if (cP.fixed_alpha && !cP.alpha_provided) {
       if constexpr (GRAM) {
         cursrc.G = cP.gram_set, cursrc.ldg = cP.ldg, cursrc.Arm = cP.basis_rm, cursrc.Acm = cP.basis_cm;
-        if (cP.reg == 2 && cP.gcv_smem) gcv_svd_shared(cP.basis_rm, cP.ld, 1, V);
+        // one basis for the whole run: its singular values stay in the warp's scratch after the first voxel
+        if (cP.reg == 2 && cP.gcv_smem && !gcv_fixed_done) gcv_svd_shared(cP.basis_rm, cP.ld, 1, V), gcv_fixed_done = true;
         stage_bulk(Gs, cP.gram_set, (unsigned)(cP.a_elems * 8));
         gram_rhs(cursrc.Arm);
       }
