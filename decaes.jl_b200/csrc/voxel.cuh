@@ -146,7 +146,7 @@ struct Src {               // where the current basis of the Gram solver lives
 #define DECAES_PRAGMA_(x) _Pragma(#x)
 #define DECAES_PRAGMA(x) DECAES_PRAGMA_(x)
 #ifndef DECAES_RESID_CHUNK
-#define DECAES_RESID_CHUNK 4  // columns per L2 round trip of the explicit residual (8: +0.5 % on cfg3, -3 % on the nT2 = 60 configs)
+#define DECAES_RESID_CHUNK 4  // columns per L2 round trip of the explicit residual (8: -0.9 % on cfg3 with today's code, -3 % on the nT2 = 60 configs)
 #endif
 #ifndef DECAES_EPG_UNROLL
 #define DECAES_EPG_UNROLL 2  // state loop of the shared-memory EPG (independent iterations: unrolling buys ILP, costs code; +1.3 % with two echoes per sweep)
@@ -884,7 +884,9 @@ struct Warp {
     int i = lc_find(t, npts);
     if (i != 0x7fffffff) return i;
     cache_solve(dexp(t), Asrc, t, hint);
-    double xi = dlog(cur_resnorm_sq()), eta = dlog(cur_seminorm_sq());
+    // the two logarithms (a software sequence each) side by side on the odd and the even lanes
+    const double lv = dlog((lane & 1) ? cur_seminorm_sq() : cur_resnorm_sq());
+    const double xi = __shfl_sync(DECAES_FULL_MASK, lv, 0), eta = __shfl_sync(DECAES_FULL_MASK, lv, 1);
     i = npts;
     if (npts < DECAES_LC_MAX) {
       if (lane == 0) pts[4 * i] = t, pts[4 * i + 1] = xi, pts[4 * i + 2] = eta, pts[4 * i + 3] = -CUDART_INF;
@@ -897,6 +899,47 @@ struct Warp {
     return i;
   }
 
+#ifndef DECAES_LC_CURV_SEQ
+  // The four points of the state are handled in PARALLEL: lanes 8 q .. 8 q + 7 own point q, scan the cached abscissae with a
+  // stride of eight and reduce inside their group by shuffles; the Menger curvature (a division and a square root, both
+  // software sequences) is then evaluated once by every lane for its own point instead of four times in a row by the whole
+  // warp.  Same arithmetic per point as the sequential scan (first index wins on ties): bit-identical curvatures.
+  __device__ __noinline__ void lc_update_curvature(const double *sx, const int *si, int npts, double tlx, double tly, double brx,
+                                      double bry, double Ctol) {
+    const int lane = this->lane;
+    VIEWG(double, lc_pts_p);
+    double *pts = lc_pts_p;
+    const int q = lane >> 3, sub = lane & 7;
+    const int pi = si[q];
+    const double x = sx[q], px = pts[4 * pi + 1], py = pts[4 * pi + 2];
+    // nearest cached abscissae on either side of x (src/lsqnonneg.jl:954-959): first index on ties
+    unsigned long long km = 0ull, kp = ~0ull;
+    int im = 0x7fffffff, ip = 0x7fffffff;
+    _Pragma("unroll 1") for (int k = sub; k < npts; k += 8) {
+      const double _x = pts[4 * k];
+      const unsigned long long kk = dkey(_x);
+      if (_x < x && kk > km) km = kk, im = k;
+      if (x < _x && kk < kp) kp = kk, ip = k;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned long long okm = __shfl_xor_sync(DECAES_FULL_MASK, km, o), okp = __shfl_xor_sync(DECAES_FULL_MASK, kp, o);
+      const int oim = __shfl_xor_sync(DECAES_FULL_MASK, im, o), oip = __shfl_xor_sync(DECAES_FULL_MASK, ip, o);
+      if (okm > km || (okm == km && oim < im)) km = okm, im = oim;
+      if (okp < kp || (okp == kp && oip < ip)) kp = okp, ip = oip;
+    }
+    double C = -CUDART_INF;
+    if (fmin(norm2(px, py, tlx, tly), norm2(px, py, brx, bry)) > Ctol) {
+      double mx = px, my = py, qx = px, qy = py;
+      if (km != 0ull) mx = pts[4 * im + 1], my = pts[4 * im + 2];
+      if (kp != ~0ull) qx = pts[4 * ip + 1], qy = pts[4 * ip + 2];
+      C = menger(mx, my, px, py, qx, qy);
+    }
+    __syncwarp();
+    if (sub == 0) pts[4 * pi + 3] = C;
+    __syncwarp();
+  }
+#else
   __device__ __noinline__ void lc_update_curvature(const double *sx, const int *si, int npts, double tlx, double tly, double brx,
                                       double bry, double Ctol) {
     const int lane = this->lane;
@@ -930,6 +973,8 @@ struct Warp {
       __syncwarp();
     }
   }
+
+#endif
 
   // mapfindmax over the curvatures: first maximum under Base.isless (NaN is maximal)
   __device__ __noinline__ int lc_argmax(int npts) {
@@ -1488,11 +1533,16 @@ struct Warp {
     double dof = (double)((m - n) > 0 ? (m - n) : 0);
     double l2 = __dmul_rn(mu, mu);
     const double *gam = g + sl.gcv_gamma;
+    GL(gam);
     int mn = m < n ? m : n;
-    for (int i = 0; i < mn; i++) {
+    // sum_i mu^2 / (gamma_i^2 + mu^2): one division per lane and pass instead of min(m, n) in a row on every lane (the sum is
+    // taken in butterfly order: ~1 ulp from the sequential one)
+    double part = 0.0;
+    _Pragma("unroll 1") for (int i = lane; i < mn; i += 32) {
       double g2 = __dmul_rn(gam[i], gam[i]);
-      dof += l2 / (g2 + l2);
+      part += l2 / (g2 + l2);
     }
+    dof += warp_sum(part);
     double gcv = r2 / __dmul_rn(dof, dof);
     gcv = fmax(gcv, (DBL_EPSILON * DBL_EPSILON) / m);
     return log(gcv);
@@ -1585,15 +1635,16 @@ struct Warp {
     double r0 = bd[i0], r1 = bd[i1], r2 = bd[i2];
     // columns in chunks of DECAES_RESID_CHUNK, every load of a chunk issued before its first fma (A lives in L2 and the loop
     // is bound by its latency); slots beyond k repeat the chunk's first column with a zero coefficient: no branches, same sums
-    _Pragma("unroll 1") for (int tb = 0; tb < k; tb += DECAES_RESID_CHUNK) {
-      double v0[DECAES_RESID_CHUNK], v1[DECAES_RESID_CHUNK];
+    constexpr int RC = DECAES_RESID_CHUNK;
+    _Pragma("unroll 1") for (int tb = 0; tb < k; tb += RC) {
+      double v0[RC], v1[RC];
 #pragma unroll
-      for (int u = 0; u < DECAES_RESID_CHUNK; u++) {
+      for (int u = 0; u < RC; u++) {
         const double *col = Acm + gws.P[tb + u < k ? tb + u : tb] * nTE;
         v0[u] = col[i0], v1[u] = col[i1];
       }
 #pragma unroll
-      for (int u = 0; u < DECAES_RESID_CHUNK; u++) {
+      for (int u = 0; u < RC; u++) {
         const double st = tb + u < k ? gws.s[tb + u < k ? tb + u : tb] : 0.0;
         r0 = fma(-v0[u], st, r0), r1 = fma(-v1[u], st, r1);
       }
