@@ -790,8 +790,6 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   // 2 = bidiagonalisation + bisection (needs the tall copy with an odd leading dimension), 1 = parallel Jacobi (A/B: DECAES_GCV_SMEM=1)
   if (P.gcv_smem && std::max(nTE, nT2) * (std::min(nTE, nT2) | 1) <= L.bd) P.gcv_smem = 2;
   if (const char *e = getenv("DECAES_GCV_SMEM")) P.gcv_smem = std::min(P.gcv_smem, atoi(e));
-  P.gcv_sturm2 = 1;
-  if (const char *e = getenv("DECAES_GCV_STURM2")) P.gcv_sturm2 = atoi(e) != 0;
   // one copy of the voxel's basis in the global scratch (column-major) unless someone needs the row-major one too: the QR
   // port (TMA source), the shuffle EPG (no on-the-fly right-hand side), the global-memory SVD of Reg = gcv
   P.need_rm = !P.gram || !P.epg_smem || (o->reg == DECAES_REG_GCV && !P.gcv_smem);

@@ -51,7 +51,6 @@ struct PipeParams {
   int need_rm;              // the voxel's basis is also kept row-major in the global scratch (0: column-major only, c = A'b comes out of the EPG)
   int gcv_smem;             // Reg = gcv: the singular values are computed in shared memory during the basis phase (2: bidiagonalisation +
                             // bisection, gcv_svdvals_bidiag; 1: parallel one-sided Jacobi, gcv_svdvals_smem; 0: global-memory Jacobi)
-  int gcv_sturm2;           // bisection of gcv_svdvals_bidiag: two Sturm pivots per reciprocal
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
   int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too: 1 = all probes, 2 = all but the seed probes
   double kkt_tau;           // screening threshold of the polish: duals above -kkt_tau * max|c| are recomputed explicitly
@@ -1319,8 +1318,60 @@ struct Warp {
   //  * left reflector k (column k, rows k..r-1): lane <-> column j > k, the reflector is read as a broadcast;
   //  * right reflector k (row k, columns k+1..c-1): lane <-> row i > k; the leading dimension c | 1 is odd, so both
   //    access directions are free of bank conflicts; two columns / rows per lane advance together;
-  //  * bisection: lane <-> singular values lane and lane + 32, all lanes take the same 54 halvings of [0, ||B||_F]
-  //    (interval 6e-17 ||B||_F), one reciprocal + one fma per off-diagonal entry and chain.
+  //  * multisection: lane <-> singular values lane and lane + 32, all lanes take the same 34 trisections of [0, ||B||_F]
+  //    (interval 6e-17 ||B||_F), two Sturm pivots per reciprocal, four independent chains per lane.
+  // One lane's share of a Householder update x -= g (v'x) v for one (TWO: two) vectors x: element t of x at o[t * os], of v at
+  // vec[t * vs] for t in [lo, hi), the leading element (index head) of v is v0.  Chunks of four elements are loaded before they
+  // are stored (the compiler cannot see that v and x never overlap).  TWO is warp-uniform (does ANY lane have a second vector:
+  // when none has, its loads would only cost shared-memory wavefronts), `two` is the lane's own answer.
+  template <bool TWO>
+  static __device__ __noinline__ void reflect_apply(double *o0, double *o1, bool two, const double *vec, int os, int vs, int head, int lo,
+                                                    int hi, double v0, double g) {
+    SH(o0);
+    SH(o1);
+    SH(vec);
+    double w0 = v0 * o0[head * os], w1 = TWO ? v0 * o1[head * os] : 0.0;
+    int t = lo;
+    _Pragma("unroll 1") for (; t + 4 <= hi; t += 4) {
+      double vv[4], a0[4], a1[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        vv[u] = vec[(t + u) * vs], a0[u] = o0[(t + u) * os];
+        if (TWO) a1[u] = o1[(t + u) * os];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        w0 = fma(vv[u], a0[u], w0);
+        if (TWO) w1 = fma(vv[u], a1[u], w1);
+      }
+    }
+    _Pragma("unroll 1") for (; t < hi; t++) {
+      w0 = fma(vec[t * vs], o0[t * os], w0);
+      if (TWO) w1 = fma(vec[t * vs], o1[t * os], w1);
+    }
+    w0 *= g, w1 *= g;
+    o0[head * os] = fma(-v0, w0, o0[head * os]);
+    if (TWO && two) o1[head * os] = fma(-v0, w1, o1[head * os]);
+    t = lo;
+    _Pragma("unroll 1") for (; t + 4 <= hi; t += 4) {
+      double vv[4], a0[4], a1[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        vv[u] = vec[(t + u) * vs], a0[u] = o0[(t + u) * os];
+        if (TWO) a1[u] = o1[(t + u) * os];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        o0[(t + u) * os] = fma(-vv[u], w0, a0[u]);
+        if (TWO && two) o1[(t + u) * os] = fma(-vv[u], w1, a1[u]);
+      }
+    }
+    _Pragma("unroll 1") for (; t < hi; t++) {
+      const double vt = vec[t * vs];
+      o0[t * os] = fma(-vt, w0, o0[t * os]);
+      if (TWO && two) o1[t * os] = fma(-vt, w1, o1[t * os]);
+    }
+  }
   // 1 / a for finite, normal |a| in [1e-150, 1e150] (the clamped Sturm pivots): the hardware seed (MUFU.RCP64H, ~20 bits) and
   // one cubic Newton step, 2^-60 relative - no range checks and no slow-path branch, so independent chains interleave
   static __device__ __forceinline__ double rcp_nr(double a) {
@@ -1361,10 +1412,9 @@ struct Warp {
     }
     __syncwarp();
     // Reflectors are kept unnormalised: v = x - beta e_1 with beta = -sign(x_0) ||x||, H = I - g v v', g = 1 / (||x|| (||x|| + |x_0|));
-    // v_0 lives in a register, the rest of v stays where x was.  The update loops load a chunk of four rows / columns before
-    // they store it (the compiler cannot see that the reflector and the updated entries never overlap).
+    // v_0 lives in a register, the rest of v stays where x was (reflect_apply).
     _Pragma("unroll 1") for (int k = 0; k < C; k++) {
-      {  // left reflector: annihilate B[k+1:R, k]
+      {  // left reflector: annihilate B[k+1:R, k]; lane <-> columns k + 1 + lane (+ 32)
         double *const colk = B + k;
         double acc = 0.0;
         _Pragma("unroll 1") for (int i = k + 1 + lane; i < R; i += 32) acc = fma(colk[i * ld], colk[i * ld], acc);
@@ -1374,44 +1424,16 @@ struct Warp {
           const double v0 = x0 + copysign(nrm, x0), g = 1.0 / (nrm * (nrm + fabs(x0)));
           __syncwarp();
           if (lane == 0) colk[k * ld] = -copysign(nrm, x0);
-          const int j0 = k + 1 + lane, j1 = j0 + 32;
+          const int j0 = k + 1 + lane;
           if (j0 < C) {
-            const bool two = j1 < C;
-            double *const c0 = B + j0, *const c1 = B + (two ? j1 : j0);
-            double w0 = v0 * c0[k * ld], w1 = v0 * c1[k * ld];
-            int i = k + 1;
-            _Pragma("unroll 1") for (; i + 4 <= R; i += 4) {
-              double vv[4], a0[4], a1[4];
-#pragma unroll
-              for (int u = 0; u < 4; u++) vv[u] = colk[(i + u) * ld], a0[u] = c0[(i + u) * ld], a1[u] = c1[(i + u) * ld];
-#pragma unroll
-              for (int u = 0; u < 4; u++) w0 = fma(vv[u], a0[u], w0), w1 = fma(vv[u], a1[u], w1);
-            }
-            _Pragma("unroll 1") for (; i < R; i++) w0 = fma(colk[i * ld], c0[i * ld], w0), w1 = fma(colk[i * ld], c1[i * ld], w1);
-            w0 *= g, w1 *= g;
-            c0[k * ld] = fma(-v0, w0, c0[k * ld]);
-            if (two) c1[k * ld] = fma(-v0, w1, c1[k * ld]);
-            i = k + 1;
-            _Pragma("unroll 1") for (; i + 4 <= R; i += 4) {
-              double vv[4], a0[4], a1[4];
-#pragma unroll
-              for (int u = 0; u < 4; u++) vv[u] = colk[(i + u) * ld], a0[u] = c0[(i + u) * ld], a1[u] = c1[(i + u) * ld];
-#pragma unroll
-              for (int u = 0; u < 4; u++) {
-                c0[(i + u) * ld] = fma(-vv[u], w0, a0[u]);
-                if (two) c1[(i + u) * ld] = fma(-vv[u], w1, a1[u]);
-              }
-            }
-            _Pragma("unroll 1") for (; i < R; i++) {
-              const double vi = colk[i * ld];
-              c0[i * ld] = fma(-vi, w0, c0[i * ld]);
-              if (two) c1[i * ld] = fma(-vi, w1, c1[i * ld]);
-            }
+            const bool two = j0 + 32 < C;
+            if (C - k - 1 > 32) reflect_apply<true>(B + j0, B + (two ? j0 + 32 : j0), two, colk, ld, ld, k, k + 1, R, v0, g);
+            else reflect_apply<false>(B + j0, B + j0, false, colk, ld, ld, k, k + 1, R, v0, g);
           }
           __syncwarp();
         }
       }
-      if (k < C - 2) {  // right reflector: annihilate B[k, k+2:C]
+      if (k < C - 2) {  // right reflector: annihilate B[k, k+2:C]; lane <-> rows k + 1 + lane (+ 32)
         double *const rowk = B + k * ld;
         double acc = 0.0;
         _Pragma("unroll 1") for (int j = k + 2 + lane; j < C; j += 32) acc = fma(rowk[j], rowk[j], acc);
@@ -1423,36 +1445,8 @@ struct Warp {
           if (lane == 0) rowk[k + 1] = -copysign(nrm, x0);
           _Pragma("unroll 1") for (int i0 = k + 1 + lane; i0 < R; i0 += 64) {
             const bool two = i0 + 32 < R;
-            double *const r0 = B + i0 * ld, *const r1 = B + (two ? i0 + 32 : i0) * ld;
-            double z0 = u0 * r0[k + 1], z1 = u0 * r1[k + 1];
-            int j = k + 2;
-            _Pragma("unroll 1") for (; j + 4 <= C; j += 4) {
-              double uu[4], a0[4], a1[4];
-#pragma unroll
-              for (int u = 0; u < 4; u++) uu[u] = rowk[j + u], a0[u] = r0[j + u], a1[u] = r1[j + u];
-#pragma unroll
-              for (int u = 0; u < 4; u++) z0 = fma(a0[u], uu[u], z0), z1 = fma(a1[u], uu[u], z1);
-            }
-            _Pragma("unroll 1") for (; j < C; j++) z0 = fma(r0[j], rowk[j], z0), z1 = fma(r1[j], rowk[j], z1);
-            z0 *= g, z1 *= g;
-            r0[k + 1] = fma(-u0, z0, r0[k + 1]);
-            if (two) r1[k + 1] = fma(-u0, z1, r1[k + 1]);
-            j = k + 2;
-            _Pragma("unroll 1") for (; j + 4 <= C; j += 4) {
-              double uu[4], a0[4], a1[4];
-#pragma unroll
-              for (int u = 0; u < 4; u++) uu[u] = rowk[j + u], a0[u] = r0[j + u], a1[u] = r1[j + u];
-#pragma unroll
-              for (int u = 0; u < 4; u++) {
-                r0[j + u] = fma(-z0, uu[u], a0[u]);
-                if (two) r1[j + u] = fma(-z1, uu[u], a1[u]);
-              }
-            }
-            _Pragma("unroll 1") for (; j < C; j++) {
-              const double uj = rowk[j];
-              r0[j] = fma(-z0, uj, r0[j]);
-              if (two) r1[j] = fma(-z1, uj, r1[j]);
-            }
+            if (R - k - 1 > 32) reflect_apply<true>(B + i0 * ld, B + (two ? i0 + 32 : i0) * ld, two, rowk, 1, 1, k + 1, k + 2, C, u0, g);
+            else reflect_apply<false>(B + i0 * ld, B + i0 * ld, false, rowk, 1, 1, k + 1, k + 2, C, u0, g);
           }
           __syncwarp();
         }
@@ -1477,46 +1471,50 @@ struct Warp {
     __syncwarp();
     // pivots below pivmin in magnitude are replaced by -pivmin (LAPACK dlaebz's safeguard; an absolute perturbation of 1e-150)
     const double bound = sqrt(fro) * 1.0000001, pivmin = 1e-150 * fmax(1.0, mx);
-    double lo0 = 0.0, hi0 = bound, lo1 = 0.0, hi1 = bound;
-    const int t0 = C + lane, t1 = C + lane + 32;  // sigma_j (ascending, 0-based) < x  <=>  #(eigenvalues < x) > C + j
-    const bool pairs = cP.gcv_sturm2 != 0;
-    _Pragma("unroll 1") for (int it = 0; it < 54; it++) {
-      const double x0 = (lo0 + hi0) / 2, x1 = (lo1 + hi1) / 2;
-      double q0 = -x0, q1 = -x1;  // first pivot: negative (x > 0)
-      int c0 = 1, c1 = 1;
-      if (pairs) {
-        // two pivots per reciprocal: with num = q_{i-1} q_i = -x q_{i-1} - b_i,  q_{i+1} = -x - b_{i+1} q_{i-1} / num and
-        // sign(q_i) = sign(num) sign(q_{i-1}); nb is odd, so the last entry takes a single step
-        _Pragma("unroll 1") for (int i = 0; i + 1 < nb; i += 2) {
-          const double ba = B[i], bb = B[i + 1];
-          double n0 = fma(-x0, q0, -ba), n1 = fma(-x1, q1, -ba);
-          if (fabs(n0) < pivmin * fabs(q0)) n0 = -pivmin * q0;  // q_i := -pivmin
-          if (fabs(n1) < pivmin * fabs(q1)) n1 = -pivmin * q1;
-          c0 += (n0 < 0.0) != (q0 < 0.0), c1 += (n1 < 0.0) != (q1 < 0.0);
-          q0 = fma(-__dmul_rn(bb, q0), rcp_nr(n0), -x0), q1 = fma(-__dmul_rn(bb, q1), rcp_nr(n1), -x1);
-          if (fabs(q0) < pivmin) q0 = -pivmin;
-          if (fabs(q1) < pivmin) q1 = -pivmin;
-          c0 += q0 < 0.0, c1 += q1 < 0.0;
-        }
-        const double bl = B[nb - 1];
-        q0 = fma(-bl, rcp_nr(q0), -x0), q1 = fma(-bl, rcp_nr(q1), -x1);
-        c0 += q0 < 0.0, c1 += q1 < 0.0;
-      } else {
-        _Pragma("unroll 2") for (int i = 0; i < nb; i++) {
-          const double bb = B[i];
-          q0 = fma(-bb, __drcp_rn(q0), -x0), q1 = fma(-bb, __drcp_rn(q1), -x1);
-          if (fabs(q0) < pivmin) q0 = -pivmin;
-          if (fabs(q1) < pivmin) q1 = -pivmin;
-          c0 += q0 < 0.0, c1 += q1 < 0.0;
+    // lane <-> singular values lane and lane + 32; every step cuts both intervals in THREE (Sturm counts at the two interior
+    // points: four independent chains per lane, the recursion is bound by the latency of its reciprocal): 34 steps shrink
+    // [0, ||B||_F] by 3^34 = 1.7e16
+    double lo[2] = {0.0, 0.0}, hi[2] = {bound, bound};
+    const int tg[2] = {C + lane, C + lane + 32};  // sigma_j (ascending, 0-based) < x  <=>  #(eigenvalues < x) > C + j
+    _Pragma("unroll 1") for (int it = 0; it < 34; it++) {
+      double x[4], q[4];
+      int c[4];
+#pragma unroll
+      for (int v = 0; v < 2; v++) {
+        const double third = (hi[v] - lo[v]) * (1.0 / 3.0);
+        x[2 * v] = lo[v] + third, x[2 * v + 1] = hi[v] - third;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) q[u] = (x[u] < pivmin) ? -pivmin : -x[u], c[u] = 1;  // first pivot: negative (x > 0)
+      // two pivots per reciprocal: with num = q_{i-1} q_i = -x q_{i-1} - b_i,  q_{i+1} = -x - b_{i+1} q_{i-1} / num and
+      // sign(q_i) = sign(num) sign(q_{i-1}); nb is odd, so the last entry takes a single step
+      _Pragma("unroll 1") for (int i = 0; i + 1 < nb; i += 2) {
+        const double ba = B[i], bb = B[i + 1];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          double nu = fma(-x[u], q[u], -ba);
+          if (fabs(nu) < pivmin * fabs(q[u])) nu = -pivmin * q[u];  // q_i := -pivmin
+          c[u] += (nu < 0.0) != (q[u] < 0.0);
+          double qn = fma(-__dmul_rn(bb, q[u]), rcp_nr(nu), -x[u]);
+          if (fabs(qn) < pivmin) qn = -pivmin;
+          c[u] += qn < 0.0;
+          q[u] = qn;
         }
       }
-      if (c0 > t0) hi0 = x0; else lo0 = x0;
-      if (c1 > t1) hi1 = x1; else lo1 = x1;
+      const double bl = B[nb - 1];
+#pragma unroll
+      for (int u = 0; u < 4; u++) c[u] += fma(-bl, rcp_nr(q[u]), -x[u]) < 0.0;
+#pragma unroll
+      for (int v = 0; v < 2; v++) {
+        if (c[2 * v] > tg[v]) hi[v] = x[2 * v];
+        else if (c[2 * v + 1] > tg[v]) lo[v] = x[2 * v], hi[v] = x[2 * v + 1];
+        else lo[v] = x[2 * v + 1];
+      }
     }
     double *gam = g + sl.gcv_gamma;
     GL(gam);
-    if (lane < C) gam[lane] = (lo0 + hi0) / 2;
-    if (lane + 32 < C) gam[lane + 32] = (lo1 + hi1) / 2;
+    if (lane < C) gam[lane] = (lo[0] + hi[0]) / 2;
+    if (lane + 32 < C) gam[lane + 32] = (lo[1] + hi[1]) / 2;
     __threadfence_block();
     __syncwarp();
   }
@@ -1836,8 +1834,8 @@ struct Warp {
     src.Arm = cP.basis_rm + (size_t)kang * cP.copy_elems;
     src.Acm = cP.basis_cm + (size_t)kang * nTE * n;
     PROF_BEGIN(5);
-    stage_bulk(Gs, src.G, (unsigned)(cP.a_elems * 8));  // TMA: G_k (lower triangle valid) -> shared memory
-    PROF_END(5);
+    stage_bulk(Gs, src.G, (unsigned)(cP.a_elems * 8));  // TMA: G_k (lower triangle valid) -> shared memory (overlapping it with the
+    PROF_END(5);                                         // right-hand side below buys nothing: profiles/r02_s4_ab_tma_overlap_vote_late_atv16.txt)
     PROF_BEGIN(0);
     gram_rhs(src.Arm);
     PROF_END(0);
