@@ -211,7 +211,8 @@ def test_refcon_angle(pkg, orc, beta, Reg):
 def test_odd_sizes(pkg, orc, nTE, nT2):
     nvox = 256
     img = orc.mock_image(nvox, nTE, 10e-3, seed=nTE)
-    for Reg, extra in [("none", {}), ("lcurve", {}), ("chi2", {"Chi2Factor": 1.05}), ("mdp", {"NoiseLevel": 1e-2})]:
+    # (gcv: the bidiagonalisation + multisection SVD on tall, wide, square and 2-column matrices)
+    for Reg, extra in [("none", {}), ("lcurve", {}), ("chi2", {"Chi2Factor": 1.05}), ("mdp", {"NoiseLevel": 1e-2}), ("gcv", {})]:
         o = orc.make_t2map_opts((nvox, 1, 1), nTE, nT2, 10e-3, Reg=Reg, ngpus=1, **extra)
         ref, _ = orc.t2map(img, o)
         got = gpu_t2map(pkg, orc, img, o, None)
