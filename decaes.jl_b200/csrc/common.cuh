@@ -9,6 +9,7 @@
 #define DECAES_FULL_MASK 0xffffffffu
 #define DECAES_MAX_ANGLES 64   // flip-angle grid is tracked in one 64-bit mask
 #define DECAES_MAX_NT2 64      // per-column flags live in one 64-bit mask
+#define DECAES_MAX_NTE 96      // lane <-> echoes lane, lane + 32, lane + 64 in the explicit residuals
 #define DECAES_LC_MAX 64       // L-curve point / state cache capacity per voxel
 #define DECAES_NCACHE 8        // NNLSTikhonovRegProblemCache slots (src/lsqnonneg.jl:396)
 #define DECAES_GROUP 4         // voxels fetched per work item = one 32-byte sector per echo

@@ -31,7 +31,7 @@ using namespace decaes;
 
 // EPG value + d/dalpha (per degree) for one (angle, T2) pair; hand forward-mode through
 // epg_impulse_response! (src/EPGdecaycurve.jl:948-1028) and |sind(alpha/2) * .| (:936-946).
-#define EPG_MAXK 40  // supports ETL <= 72
+#define EPG_MAXK 52  // phase states kept per curve: supports ETL <= DECAES_MAX_NTE (ETL - ETL / 2 + 1 = 49 at 96 echoes)
 struct Dual {
   double v, d;
 };
@@ -375,7 +375,7 @@ __global__ void mock_image_kernel(double *image, long long nvox, long long strid
   double T22 = 50e-3 + (100e-3 - 50e-3) * urand(seed, gid, 2);
   double alpha = 120.0 + 60.0 * urand(seed, gid, 3);
   double E1 = exp(-(TE / 2) / T1);
-  double d1[72], d2[72], dd[72];
+  double d1[DECAES_MAX_NTE], d2[DECAES_MAX_NTE], dd[DECAES_MAX_NTE];
   epg_curve_jac(nTE, alpha, E1, exp(-(TE / 2) / T21), d1, dd, 1);
   epg_curve_jac(nTE, alpha, E1, exp(-(TE / 2) / T22), d2, dd, 1);
   for (int k = 0; k < nTE; k++) {
@@ -442,7 +442,7 @@ static int validate_map(const decaes_t2map_opts *o) {
     return fail(DECAES_EINVAL, "Fixed flip angle must be in the range [0, 180]");
   if (o->nT2 > DECAES_MAX_NT2) return fail(DECAES_EUNSUPPORTED, "nT2 > %d is not supported", DECAES_MAX_NT2);
   if (o->nRefAngles > DECAES_MAX_ANGLES) return fail(DECAES_EUNSUPPORTED, "nRefAngles > %d is not supported", DECAES_MAX_ANGLES);
-  if (o->nTE > 72) return fail(DECAES_EUNSUPPORTED, "nTE > 72 is not supported");
+  if (o->nTE > DECAES_MAX_NTE) return fail(DECAES_EUNSUPPORTED, "nTE > %d is not supported", DECAES_MAX_NTE);
   return DECAES_OK;
 }
 static int validate_part(const decaes_t2part_opts *o) {
@@ -1088,7 +1088,7 @@ int decaes_t2part_device(const double *d_dist, int64_t nvox, int64_t stride, con
 
 int decaes_mock_image_device(double *d_image, int64_t nvox, int64_t stride, int64_t first_voxel, int32_t nTE,
                              double TE, double T1, double SNR, uint64_t seed, void *stream) {
-  if (!d_image || nvox < 0 || stride < nvox || nTE < 4 || nTE > 72) return fail(DECAES_EINVAL, "bad arguments");
+  if (!d_image || nvox < 0 || stride < nvox || nTE < 4 || nTE > DECAES_MAX_NTE) return fail(DECAES_EINVAL, "bad arguments");
   if (nvox == 0) return DECAES_OK;
   double sigma = std::pow(10.0, -SNR / 20);
   mock_image_kernel<<<(unsigned)((nvox + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_image, nvox, stride, first_voxel,

@@ -51,7 +51,7 @@ typedef enum {
   DECAES_OK = 0,
   DECAES_EINVAL = -1,       /* option fails a T2mapOptions/T2partOptions assertion (src/types.jl:28-84,148-168) */
   DECAES_ECUDA = -2,        /* CUDA runtime error / no device */
-  DECAES_EUNSUPPORTED = -3, /* size outside the accelerated path (nT2 > 64, nRefAngles > 64, nTE > 72) */
+  DECAES_EUNSUPPORTED = -3, /* size outside the accelerated path (nT2 > 64, nRefAngles > 64, nTE > 96) */
   DECAES_ENOMEM = -4
 } decaes_status;
 

@@ -98,7 +98,7 @@ function last_stats()
 end
 
 const DECAES_ECUDA = Cint(-2)        # no usable device / CUDA error
-const DECAES_EUNSUPPORTED = Cint(-3) # outside the accelerated path: nT2 > 64, nRefAngles > 64, nTE > 72
+const DECAES_EUNSUPPORTED = Cint(-3) # outside the accelerated path: nT2 > 64, nRefAngles > 64, nTE > 96
 
 last_error() = unsafe_string(ccall((:decaes_last_error, libdecaes_cuda), Cstring, ()))
 
@@ -221,7 +221,7 @@ release() = ccall((:decaes_release, libdecaes_cuda), Cvoid, ())
 # Routing the public Float64 entry points through the GPU library is OPT-IN: `DECAESCUDA.enable!()` adds the two
 # more specific methods below (inside DECAES itself the same thing is the two-line patch of INTEGRATION.md; adding
 # methods to another package's functions at load time would break precompilation on Julia >= 1.10).  Calls the library
-# does not accelerate - sizes beyond nT2 = 64 / nRefAngles = 64 / nTE = 72, a machine without a GPU - fall back to
+# does not accelerate - sizes beyond nT2 = 64 / nRefAngles = 64 / nTE = 96, a machine without a GPU - fall back to
 # DECAES.jl's CPU worker loop through `invoke`, so nothing the reference handles starts to throw.
 # `legacy = true` (sampled FITPACK spline for the flip angle and for the chi2 root, src/splines.jl:419-446,
 # src/lsqnonneg.jl:595-636) runs on the GPU as well; an all-Float32 `T2mapSEcorr(image::Array{Float32,4})` keeps

@@ -71,6 +71,9 @@ def test_validation_through_the_abi(pkg, orc):
     big = orc.make_t2map_opts((nvox, 1, 1), 32, 65, 10e-3)  # nT2 > 64: outside the accelerated path
     assert L.decaes_t2map(img.ctypes.data, C.byref(big), None, C.byref(out)) == -3
     assert b"nT2 > 64" in L.decaes_last_error()
+    long_train = orc.make_t2map_opts((nvox, 1, 1), 97, 40, 10e-3)  # nTE > 96: outside the accelerated path
+    assert L.decaes_t2map(img.ctypes.data, C.byref(long_train), None, C.byref(out)) == -3
+    assert b"nTE > 96" in L.decaes_last_error()
     good = orc.make_t2map_opts((nvox, 1, 1), 32, 40, 10e-3)
     noout = pkg._abi.T2mapOut()
     assert L.decaes_t2map(img.ctypes.data, C.byref(good), None, C.byref(noout)) == -1

@@ -207,7 +207,7 @@ def test_refcon_angle(pkg, orc, beta, Reg):
     assert rep["frac_out_of_tolerance_same_mu"] <= 0.02 and rep["mu_flip_frac"] <= flip_bound, rep
 
 
-@pytest.mark.parametrize("nTE,nT2", [(4, 2), (5, 3), (8, 8), (47, 47), (64, 60)])
+@pytest.mark.parametrize("nTE,nT2", [(4, 2), (5, 3), (8, 8), (47, 47), (64, 60), (80, 40), (96, 40)])
 def test_odd_sizes(pkg, orc, nTE, nT2):
     nvox = 256
     img = orc.mock_image(nvox, nTE, 10e-3, seed=nTE)
