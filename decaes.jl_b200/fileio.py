@@ -139,7 +139,10 @@ def load_image(filename, ndims=4):
         raw, slope, inter = read_nifti(filename)
         if slope == 0:  # "if scl_slope == 0, data is not scaled and raw data should be returned"
             slope, inter = 1.0, 0.0
-        data = raw.astype(np.float64) * slope + inter if (slope != 1.0 or inter != 0.0) else raw
+        # `nii.raw .* scl_slope .+ scl_inter` (src/main.jl:599) with Float32 header fields: Julia computes in
+        # promote_type(eltype(raw), Float32) - Float32 for integer and Float32 volumes, Float64 for Float64 ones
+        ct = np.float64 if raw.dtype == np.float64 else np.float32
+        data = raw.astype(ct) * ct(slope) + ct(inter)
     elif ext in (".par", ".xml", ".rec"):
         raise ValueError(f"{filename}: Philips PAR/REC/XML files are not supported by this host mirror; convert to NIfTI")
     else:
