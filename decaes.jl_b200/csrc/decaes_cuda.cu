@@ -708,6 +708,8 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.kkt_tau = 1e-8;  // two orders of magnitude above the noise of the normal-equation duals (1e-6: three candidates per solve instead of one)
   if (const char *e = getenv("DECAES_KKT_TAU")) P.kkt_tau = atof(e);
   if (const char *e = getenv("DECAES_FA_REFINE")) P.fa_refine = atoi(e);
+  P.warm_ones = 1;
+  if (const char *e = getenv("DECAES_WARM_ONES")) P.warm_ones = atoi(e) != 0;
   P.lc_hints = 15;  // bit 2: the full-set start is a direct Cholesky solve (gram_dense_solve); bit 3: dilated sets for points 2 and 3
   if (const char *e = getenv("DECAES_LC_HINTS")) P.lc_hints = atoi(e) & 15;  // bit 3: dilated sets for the second / third point
   // In-phase votes (voxel.cuh: cta_or): flip-angle probes and L-curve steps are uniform enough that keeping the warps

@@ -51,6 +51,7 @@ struct PipeParams {
   int need_rm;              // the voxel's basis is also kept row-major in the global scratch (0: column-major only, c = A'b comes out of the EPG)
   int gcv_smem;             // Reg = gcv: the singular values are computed in shared memory during the basis phase (2: bidiagonalisation +
                             // bisection, gcv_svdvals_bidiag; 1: parallel one-sided Jacobi, gcv_svdvals_smem; 0: global-memory Jacobi)
+  int warm_ones;            // warm starts of the Tikhonov solves begin at x = 1 on the inherited set (0: at the cached solution of the nearest mu)
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
   int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too: 1 = all probes, 2 = all but the seed probes
   double kkt_tau;           // screening threshold of the polish: duals above -kkt_tau * max|c| are recomputed explicitly
@@ -2039,7 +2040,6 @@ struct Warp {
       if (isl && !isnan(mui) && slot_mask[lane] != 0ull) key = (unsigned long long)__double_as_longlong(fabs(lmu - slot_lmu[lane]));
       const int nearest = warp_argmin_bits(key, lane, best);
       if (best != ~0ull) {
-        const double *sx = slots_x_p + nearest * n;
         const unsigned long long m0 = slot_mask[nearest];
         wmask = m0;
         if (hint >= 3) {
@@ -2048,8 +2048,16 @@ struct Warp {
           _Pragma("unroll 1") for (int d = 0; d < hint - 2; d++) wmask |= (wmask << 1) | (wmask >> 1);
           if (n < 64) wmask &= (1ull << n) - 1ull;
         }
-        // (the new columns start at a small positive value: a feasible interior point, so a wrong guess leaves alone)
-        _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = ((m0 >> j) & 1ull) ? sx[j] : (((wmask >> j) & 1ull) ? 1e-3 : 0.0);
+        // A feasible interior point on the inherited set: only the final minimiser (unique for mu > 0) matters, so the warm start
+        // does not fetch the cached solution of that mu from the spilled table (one L2 round trip per solve; DECAES_WARM_ONES=0:
+        // start from the cached solution - same parity figures, -0.3 %, profiles/r02_s4_ab_warm_start_from_ones.txt).  New
+        // columns of a dilated set start at a small positive value, so that a wrong guess leaves at once.
+        if (cP.warm_ones) {
+          _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = ((m0 >> j) & 1ull) ? 1.0 : (((wmask >> j) & 1ull) ? 1e-3 : 0.0);
+        } else {
+          const double *sx = slots_x_p + nearest * n;
+          _Pragma("unroll 1") for (int j = lane; j < n; j += 32) gws.x[j] = ((m0 >> j) & 1ull) ? sx[j] : (((wmask >> j) & 1ull) ? 1e-3 : 0.0);
+        }
         __syncwarp();
       }
     }
