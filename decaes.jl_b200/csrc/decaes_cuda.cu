@@ -715,7 +715,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   // In-phase votes (voxel.cuh: cta_or): flip-angle probes and L-curve steps are uniform enough that keeping the warps
   // in step pays (cfg3: +20 %, cfg1: +13 %); the four initial L-curve points and the Brent searches vary too much between
   // voxels (-1 % / -6 %).  With few warps per SM (nT2 = 60: six) there is little instruction-cache pressure to relieve
-  // and the votes only cost (cfg4 / cfg5: -2 to -3 %): decided below, once the CTA shape is known.
+  // and the votes inside the searches only cost: decided below, once the CTA shape is known.
   P.step_sync = 3;
   if (const char *e = getenv("DECAES_SYNC_MASK")) P.sync_mask = atoi(e);
   P.ldg = (nT2 + 1) | 1;  // one array holds the lower triangle of G and, above it, M = L^-1 (gram.cuh)
@@ -826,7 +826,10 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   if (const char *e = getenv("DECAES_WARPS_PER_CTA")) wpc = std::max(1, std::min(wpc, atoi(e)));
   if (wpc < 1) return fail(DECAES_EUNSUPPORTED, "not enough shared memory for one warp");
   P.warps_per_cta = wpc, P.smem_per_warp = plan->smem_bytes;
-  if (wpc < 9) P.step_sync = 0;
+  // few warps per SM (nT2 = 60: six): the vote before every flip-angle probe still pays with today's code (cfg4-chi2 +2.3 %,
+  // cfg5 +0.5 %; Reg = gcv -1.4 %: off there), the votes inside the regularised searches do not
+  // (profiles/r02_s4_ab_votes_six_warps.txt)
+  if (wpc < 9) P.step_sync &= (o->reg == DECAES_REG_GCV) ? 0 : 1;
   if (const char *e = getenv("DECAES_STEP_SYNC")) P.step_sync = atoi(e) & 15;
   if (fixed || o->alpha_provided) P.step_sync &= ~1;
   if (o->reg != DECAES_REG_LCURVE) P.step_sync &= ~6;
