@@ -789,7 +789,7 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   P.epg_smem = P.gram && 3 * P.epg_kmax * P.epg_lanes <= L.bd;
   if (const char *e = getenv("DECAES_EPG_SMEM")) P.epg_smem = P.epg_smem && atoi(e);
   P.gcv_smem = P.gram && o->reg == DECAES_REG_GCV && nTE * nT2 <= L.bd && std::min(nTE, nT2) <= 64;
-  // 2 = bidiagonalisation + bisection (needs the tall copy with an odd leading dimension), 1 = parallel Jacobi (A/B: DECAES_GCV_SMEM=1)
+  // 2 = bidiagonalisation + multisection (needs the tall copy with an odd leading dimension), 1 = parallel Jacobi (A/B: DECAES_GCV_SMEM=1)
   if (P.gcv_smem && std::max(nTE, nT2) * (std::min(nTE, nT2) | 1) <= L.bd) P.gcv_smem = 2;
   if (const char *e = getenv("DECAES_GCV_SMEM")) P.gcv_smem = std::min(P.gcv_smem, atoi(e));
   // one copy of the voxel's basis in the global scratch (column-major) unless someone needs the row-major one too: the QR

@@ -50,7 +50,7 @@ struct PipeParams {
   int epg_fuse;             // shared-memory EPG: two echoes per sweep over the states
   int need_rm;              // the voxel's basis is also kept row-major in the global scratch (0: column-major only, c = A'b comes out of the EPG)
   int gcv_smem;             // Reg = gcv: the singular values are computed in shared memory during the basis phase (2: bidiagonalisation +
-                            // bisection, gcv_svdvals_bidiag; 1: parallel one-sided Jacobi, gcv_svdvals_smem; 0: global-memory Jacobi)
+                            // multisection, gcv_svdvals_bidiag; 1: parallel one-sided Jacobi, gcv_svdvals_smem; 0: global-memory Jacobi)
   int warm_ones;            // warm starts of the Tikhonov solves begin at x = 1 on the inherited set (0: at the cached solution of the nearest mu)
   int refine_tikh;          // polish every Tikhonov solve with one refinement step (Gram solver)
   int fa_polish;            // KKT polish (explicit duals) on the flip-angle probes too: 1 = all probes, 2 = all but the seed probes
@@ -1312,7 +1312,7 @@ struct Warp {
   }
 
   // Singular values for Reg = gcv, third version (PipeParams::gcv_smem == 2): Golub-Kahan Householder bidiagonalisation of the
-  // tall r x c copy in shared memory (4 r c^2 / 3 flops instead of ~10 Jacobi sweeps of 6 r c^2 each), then bisection on the
+  // tall r x c copy in shared memory (4 r c^2 / 3 flops instead of ~10 Jacobi sweeps of 6 r c^2 each), then multisection on the
   // Sturm counts of the Golub-Kahan tridiagonal form of the bidiagonal (order 2c, zero diagonal, off-diagonals d1 e1 d2 e2 ...:
   // its eigenvalues are -sigma_c .. -sigma_1, sigma_1 .. sigma_c).  This is the route LAPACK takes as well (dgebrd + a bidiagonal
   // solver; the reference's dgesdd_, src/utils.jl:103-134): backward stable, every sigma to a few eps * sigma_max.
