@@ -41,6 +41,11 @@ def test_nifti_scaling_rule_and_big_endian(fio, tmp_path):
     f = str(tmp_path / "s.nii")
     fio.save_nifti(f, a, scl_slope=0.5, scl_inter=10.0)
     np.testing.assert_allclose(fio.load_image(f, 3), a * 0.5 + 10.0)
+    # the reference scales in promote_type(eltype(raw), Float32) (src/main.jl:599): Float32 arithmetic for integer volumes
+    fio.save_nifti(f, a, scl_slope=0.1, scl_inter=0.3)
+    want = (a.astype(np.float32) * np.float32(0.1) + np.float32(0.3)).astype(np.float64)
+    np.testing.assert_array_equal(fio.load_image(f, 3), want)
+    assert not np.array_equal(want, a * 0.1 + 0.3)  # ... which is not what Float64 arithmetic gives
     fio.save_nifti(f, a, scl_slope=0.0, scl_inter=7.0)  # slope 0: "data is not scaled", raw data returned
     np.testing.assert_array_equal(fio.load_image(f, 3), a.astype(float))
     # hand-made big-endian file
