@@ -716,7 +716,8 @@ static int make_plan(const decaes_t2map_opts *o, const decaes_t2part_opts *part,
   // in step pays (cfg3: +20 %, cfg1: +13 %); the four initial L-curve points and the Brent searches vary too much between
   // voxels (-1 % / -6 %).  With few warps per SM (nT2 = 60: six) there is little instruction-cache pressure to relieve
   // and the votes inside the searches only cost: decided below, once the CTA shape is known.
-  P.step_sync = 3;
+  P.step_sync = 7;  // (bit 2, the four initial L-curve points: -1 % when first tried, +0.5 % on cfg3 / +1.0 % on cfg2 with the final kernel,
+                    //  profiles/r02_s4_ab_votes_initial_points.txt)
   if (const char *e = getenv("DECAES_SYNC_MASK")) P.sync_mask = atoi(e);
   P.ldg = (nT2 + 1) | 1;  // one array holds the lower triangle of G and, above it, M = L^-1 (gram.cuh)
   if (P.gram) P.a_elems = nT2 * P.ldg;
